@@ -1,0 +1,66 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY -- never imported by the product package.
+
+Executes the reference's OWN hot-path files, unmodified, from the read-only checkout at
+/root/reference (this container only; the directory does not exist on the GPU box):
+
+    dynamics/dynamics.py, transformations/transformations.py, transformations/poses.py,
+    planners/joint_position_planner.py
+
+Their third-party imports that are absent from the image (`liegroups`, `mujoco`,
+`omegaconf`) are satisfied by the shims in oracle/shims/ (see the headers there).  The
+modules are imported under private names and every sys.path / sys.modules change is
+undone afterwards, so the product's own `dynamics` / `transformations` drop-in packages
+are never shadowed.
+
+Used by oracle/gen_golden.py (to produce tests/golden/*.npz) and by the `not gpu` tests
+that validate oracle/dynamics_oracle.py against the reference itself.
+"""
+import importlib
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("RBM_REFERENCE_ROOT", "/root/reference")
+_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+_SHADOWED = ("dynamics", "transformations", "planners", "utilities", "liegroups", "mujoco", "omegaconf")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "dynamics", "dynamics.py"))
+
+
+class ReferenceModules:
+    """Namespace holding the reference modules (`.dynamics`, `.transformations`, `.planner`, `.liegroups`)."""
+
+
+_cache = None
+
+
+def load() -> ReferenceModules:
+    """Import the reference's modules on top of the shims; returns a namespace of module objects."""
+    global _cache
+    if _cache is not None:
+        return _cache
+    if not available():
+        raise FileNotFoundError(f"reference checkout not found at {REFERENCE_ROOT}")
+
+    saved_path = list(sys.path)
+    saved_mods = {k: v for k, v in sys.modules.items() if k.split(".")[0] in _SHADOWED}
+    for k in saved_mods:
+        del sys.modules[k]
+    try:
+        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.insert(0, _SHIMS)
+        ns = ReferenceModules()
+        ns.liegroups = importlib.import_module("liegroups")
+        ns.transformations = importlib.import_module("transformations")
+        ns.dynamics = importlib.import_module("dynamics")
+        # planners/__init__.py star-imports the planner module
+        ns.planner = importlib.import_module("planners.joint_position_planner")
+        assert os.path.realpath(ns.dynamics.__file__).startswith(os.path.realpath(REFERENCE_ROOT))
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in _SHADOWED]:
+            del sys.modules[k]
+        sys.modules.update(saved_mods)
+        sys.path[:] = saved_path
+    _cache = ns
+    return ns
