@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the batched inverse-dynamics hot path (BASELINE.json metric: RNEA samples/s, % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f64|f32] [--samples B]
+    python bench.py --impl reference ...        # the reference's CPU algorithm (oracle port) on the host cores
+
+A "step" is one pass of the fused RNEA kernel over one resident batch of B synthetic (q, qd, qdd) samples
+(BASELINE.json configs[1]: B = 2^20, fp64, the base.yaml manipulator + target object).  Under torchrun every rank
+owns its own B samples (weak scaling, no data-path collective: samples are independent); the timed region is
+bracketed by barrier + synchronize, device time is taken with CUDA events and the max over ranks is reported.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rnea_samples_per_s"
+UNIT = "samples/s"
+WORKLOAD = "configs[1]: batched inverse dynamics, 2^20 synthetic (q,qd,qdd) samples, base.yaml manipulator (sequential.xml) + hammer target"
+
+
+def sample_states(rng, n):
+    """SURVEY.md 8(d) config-2 distribution."""
+    q = np.concatenate([rng.uniform(-1.5, 2.5, (n, 3)), rng.uniform(-6 * np.pi, 6 * np.pi, (n, 3))], axis=1)
+    qd = rng.standard_normal((n, 6)) * np.array([1, 1, 1, 3, 3, 3.0])
+    qdd = rng.standard_normal((n, 6)) * np.array([3, 3, 3, 10, 10, 10.0])
+    return np.stack([q, qd, qdd], axis=1)
+
+
+def load_constants():
+    from rigid_body_manipulation_b200 import model as rbm_model
+
+    return rbm_model.load_packaged("sequential", "hammer")
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi based, as the profiling recipe asks) during the timed region
+# --------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self._stop.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:  # pragma: no cover - depends on the box
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=2)
+
+    def summary(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "n_samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's per-sample algorithm on all host cores
+# --------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    consts, trajs = args
+    from oracle import rnea_oracle as ro
+
+    hposes = [ro.SE3(ro.SO3(np.array(r[:9]).reshape(3, 3)), np.array(r[9:])) for r in consts["hposes_Rt"]]
+    t0 = time.perf_counter()
+    acc = 0.0
+    for tr in trajs:
+        tau, _, _, _ = ro.inverse(tr, hposes, consts["simats"], consts["uscrews"], consts["twist_0"], consts["dtwist_0"])
+        acc += float(tau[0])
+    return time.perf_counter() - t0, acc
+
+
+def cpu_reference_rate(consts, n_samples, cores=None, pool=None):
+    """samples/s of the reference's algorithm (per-sample numpy + liegroups ops, oracle/rnea_oracle.py) on `cores` processes."""
+    import multiprocessing as mp
+
+    cores = cores or os.cpu_count() or 1
+    trajs = sample_states(np.random.default_rng(123), n_samples)
+    parts = [trajs[i::cores] for i in range(cores)]
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores)
+    try:
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(consts, p) for p in parts])
+        wall = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close()
+            pool.join()
+    return n_samples / wall, cores, wall
+
+
+def consts_dict(c):
+    return dict(hposes_Rt=c.hposes_Rt, simats=c.simats, uscrews=c.uscrews, twist_0=c.twist_0, dtwist_0=c.dtwist_0)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    c = load_constants()
+    consts = consts_dict(c)
+    cores = os.cpu_count() or 1
+    per_step = args.cpu_samples if args.cpu_samples > 0 else 2000 * cores
+    pool = mp.get_context("fork").Pool(cores)
+    try:
+        for _ in range(args.warmup):
+            cpu_reference_rate(consts, max(cores * 50, per_step // 10), cores, pool)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_reference_rate(consts, per_step, cores, pool)
+        wall = time.perf_counter() - t0
+    finally:
+        pool.close()
+        pool.join()
+    value = per_step * args.steps / wall
+    sample = f"{per_step} samples/step of the configs[1] distribution, per-sample oracle port (oracle/rnea_oracle.py) over {cores} processes"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "batch_per_step": per_step, "layout": "AoS (3,6) per sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from rigid_body_manipulation_b200.engine import Model
+
+    c = load_constants()
+    model = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, pose_sen_llj=c.pose_sen_Rt, device=local)
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    B = args.samples
+    traj_host = sample_states(np.random.default_rng(1000 + rank), B).astype(np.float64 if args.dtype == "f64" else np.float32)
+    traj_pinned = torch.as_tensor(traj_host).pin_memory()
+    esize = 8 if args.dtype == "f64" else 4
+    alg_bytes = 24 * esize * B  # 18 scalars read + 6 written per sample
+    # L2 rule: rotate over enough independent buffer sets that the data touched between two uses of the same set
+    # exceeds 3x the 126 MB L2, so no timed launch can be served from cache
+    nset = max(2, int(np.ceil(3 * 126e6 / alg_bytes)) + 1)
+    dev = torch.as_tensor(traj_host, device="cuda")
+    sets = []
+    for i in range(nset):
+        q, qd, qdd = (dev[:, k, :].t().contiguous() for k in range(3))
+        if i:  # distinct values per set (cheap perturbation), same distribution
+            q, qd, qdd = q + 1e-3 * i, qd * (1 + 1e-3 * i), qdd * (1 - 1e-3 * i)
+        sets.append((q, qd, qdd, torch.empty_like(q)))
+    del dev
+    step_no = [0]
+
+    def one_step():
+        q, qd, qdd, tau = sets[step_no[0] % nset]
+        step_no[0] += 1
+        model.rnea(q, qd, qdd, tau=tau)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        # keep the sampler alive for >= ~0.3 s so it sees the loaded clocks: untimed extra launches first
+        t_end = time.perf_counter() + 0.3
+        while time.perf_counter() < t_end:
+            one_step()
+        barrier()
+        e0.record()
+        for a, b in evs:
+            a.record()
+            one_step()
+            b.record()
+        e1.record()
+        barrier()
+    total_ms = e0.elapsed_time(e1)
+    kern_ms = [a.elapsed_time(b) for a, b in evs]
+    t = torch.tensor([total_ms, float(np.mean(kern_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms_avg = t.tolist()
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host API (pinned host buffers, H2D + kernel + D2H inside the timed region) ----
+    tau_host = torch.empty((B, 6), dtype=tdt).pin_memory()
+    for _ in range(max(1, min(args.warmup, 3))):
+        model.rnea_host(traj_pinned, tau=tau_host)
+    e2e_steps = max(1, min(args.steps, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        model.rnea_host(traj_pinned, tau=tau_host)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / t.item()
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = alg_bytes / (kern_ms_avg * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(f"rnea_{args.dtype}_bytes_per_launch_at_{B}")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "layout": "SoA [3][6][B] resident in HBM", "kernel_path": model.kernel_path,
+                       "l2_policy": f"{nset} rotating buffer sets x {alg_bytes / 1e6:.0f} MB: >= {((nset - 1) * alg_bytes) / 1e6:.0f} MB touched between reuses (L2 = 126 MB)",
+                       "parallelism": f"samples sharded x{world}, no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "kernel_ms": kern_ms_avg, "algorithmic_bytes_per_launch": alg_bytes},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 18 * esize * B, "d2h_bytes_per_step": 6 * esize * B,
+                    "api": "Model.rnea_host -> rbm_rnea_host_* (pinned host AoS in, pinned host out)", "steps": e2e_steps},
+            "gpu_launches": args.steps,
+            "clocks": clk.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            consts = consts_dict(c)
+            cores = os.cpu_count() or 1
+            n_cpu = args.cpu_samples if args.cpu_samples > 0 else 1500 * cores
+            v, cores, wall = cpu_reference_rate(consts, n_cpu, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n_cpu} samples of the same distribution, per-sample oracle port of reference dynamics.inverse, {wall:.1f} s wall"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--samples", type=int, default=1 << 20, help="samples per GPU per step")
+    ap.add_argument("--cpu-samples", type=int, default=0, help="CPU baseline sample count (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

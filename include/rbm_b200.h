@@ -1,0 +1,113 @@
+/* rbm_b200.h -- C ABI of librbm_b200.so: batched rigid-body inverse dynamics on NVIDIA B200 (sm_100a).
+ *
+ * The reference (barikata1984/rigid-body-manipulation) has NO FFI layer: its hot path is a set of plain
+ * Python module functions (dynamics/dynamics.py, transformations/transformations.py) working on numpy
+ * arrays and liegroups objects.  This header is therefore the boundary a maintainer would bind from
+ * Python with ctypes (INTEGRATION.md shows the stub); each entry point names the reference function
+ * (file:line) it replaces.  Conventions:
+ *
+ *   - plain pointers and sizes only; no C++ / torch types
+ *   - model constants are HOST pointers (tiny, copied once); batch buffers are DEVICE pointers unless the
+ *     function name ends in _host
+ *   - twists / wrenches are 6-vectors in [linear(3); angular(3)] order, as in the reference (liegroups order)
+ *   - poses are 12 scalars: rotation row-major (9) then translation (3)
+ *   - SoA batch layout: element (j, s) of a [k][ld] array is at base[j*ld + s], s = sample index < n <= ld
+ *   - AoS batch layout mirrors the reference's `traj` argument: traj[s][3][nj] = (q, qd, qdd) rows
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream);
+ *     return value 0 = ok, negative = rbm_status; the message is in rbm_last_error_string()
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with RBM_ERR_CUDA
+ */
+#ifndef RBM_B200_H
+#define RBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define RBM_API __attribute__((visibility("default")))
+#else
+#define RBM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rbm_model rbm_model; /* opaque: model constants resident on one device */
+
+typedef enum rbm_status {
+  RBM_OK = 0,
+  RBM_ERR_INVALID = -1,     /* bad argument (maps to AssertionError / ValueError in the Python shim) */
+  RBM_ERR_CUDA = -2,        /* CUDA runtime error, incl. "no device" */
+  RBM_ERR_UNSUPPORTED = -3, /* e.g. nj > RBM_MAX_JOINTS */
+  RBM_ERR_NCCL = -4
+} rbm_status;
+
+enum { RBM_MAX_JOINTS_ABI = 16 };
+
+/* rbm_model_create flags */
+enum {
+  RBM_FLAG_FORCE_GENERIC = 1 /* never select a structure-specialised kernel */
+};
+
+/* kernel path chosen for a model (rbm_model_kernel_path) */
+enum {
+  RBM_PATH_GENERIC = 0,   /* any chain: dense inertias, arbitrary screws / poses (shared-memory parameters) */
+  RBM_PATH_SEQ_ISO = 1,   /* the reference's sequential.xml structure, links 1-5 isotropic, link 6 rigid body */
+  RBM_PATH_SEQ_RIGID = 2  /* same kinematic structure, every link a general rigid body */
+};
+
+RBM_API const char* rbm_version(void);
+RBM_API const char* rbm_last_error_string(void); /* thread-local */
+RBM_API int rbm_device_count(void);              /* 0 when no CUDA device / driver is present */
+
+/* ---- model ------------------------------------------------------------------------------------------
+ * Binds the arguments that reference core/simulate.py:150-156 binds with functools.partial onto
+ * dynamics.inverse (dynamics/dynamics.py:109-118):
+ *   hposes_Rt  [(nj+1)][12]  hposes_body_parent (entry 0 unused, dynamics.py:125)
+ *   simats     [(nj+1)][36]  simats_body, row-major 6x6 (entry 0 unused, dynamics.py:144)
+ *   uscrews    [nj][6]       uscrews_body
+ *   twist_0, dtwist_0 [6]
+ *   wrench_tip [6] or NULL (= zeros, dynamics.py:116);  pose_tip_Rt [12] or NULL (= identity, :117)
+ *   pose_sen_Rt [12] or NULL (= identity): static pose of the F/T sensor frame w.r.t. the last link's joint
+ *                frame, pose_sen_llj of core/simulate.py:202 (used by the regressor entry points only)
+ * The constants are copied; the caller keeps ownership of its arrays.  `device` is the CUDA ordinal. */
+RBM_API int rbm_model_create(int nj, const double* hposes_Rt, const double* simats, const double* uscrews, const double* twist_0,
+                     const double* dtwist_0, const double* wrench_tip, const double* pose_tip_Rt, const double* pose_sen_Rt,
+                     unsigned flags, int device, rbm_model** out);
+RBM_API void rbm_model_destroy(rbm_model* m);
+RBM_API int rbm_model_num_joints(const rbm_model* m);
+RBM_API int rbm_model_kernel_path(const rbm_model* m);
+
+/* ---- inverse dynamics -------------------------------------------------------------------------------
+ * Batched dynamics.inverse (dynamics/dynamics.py:109-157): tau[j][s] for every sample s.
+ *   q, qd, qdd : [nj][ld]   tau : [nj][ld]
+ *   twist_last, dtwist_last : [6][ld] or NULL -- V and dV of the last link (twists[nj], dtwists[nj] of
+ *   the reference's return value; the only entries core/simulate.py:203,206 reads). */
+RBM_API int rbm_rnea_f64(const rbm_model* m, const double* q, const double* qd, const double* qdd, double* tau, double* twist_last,
+                 double* dtwist_last, int64_t n, int64_t ld, void* stream);
+RBM_API int rbm_rnea_f32(const rbm_model* m, const float* q, const float* qd, const float* qdd, float* tau, float* twist_last,
+                 float* dtwist_last, int64_t n, int64_t ld, void* stream);
+
+/* Same, array-of-samples layout of the reference's own argument: traj [n][3][nj] -> tau [n][nj]. */
+RBM_API int rbm_rnea_aos_f64(const rbm_model* m, const double* traj, double* tau, int64_t n, void* stream);
+RBM_API int rbm_rnea_aos_f32(const rbm_model* m, const float* traj, float* tau, int64_t n, void* stream);
+
+/* Full return value of dynamics.inverse (dynamics.py:157) per sample, AoS:
+ *   traj [n][3][nj] -> tau [n][nj], poses [n][nj][12] (T_{i,i-1}, dynamics.py:126; the appended tip pose is the
+ *   model's constant), twists [n][nj+1][6], dtwists [n][nj+1][6] (entry 0 = twist_0 / dtwist_0).
+ *   Any of poses / twists+dtwists may be NULL (twists and dtwists only together). */
+RBM_API int rbm_rnea_full_f64(const rbm_model* m, const double* traj, double* tau, double* poses, double* twists, double* dtwists,
+                      int64_t n, void* stream);
+
+/* End-to-end convenience for host callers (the `e2e` measurement): traj_host [n][3][nj] and tau_host [n][nj] are HOST
+ * buffers (pinned memory gives full PCIe rate); copies host->device, runs the AoS kernel and copies back in
+ * `chunk`-sample pieces on internal streams so transfers overlap compute.  Synchronous: returns when tau_host is
+ * complete.  chunk <= 0 picks a default. */
+RBM_API int rbm_rnea_host_f64(const rbm_model* m, const double* traj_host, double* tau_host, int64_t n, int64_t chunk);
+RBM_API int rbm_rnea_host_f32(const rbm_model* m, const float* traj_host, float* tau_host, int64_t n, int64_t chunk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBM_B200_H */

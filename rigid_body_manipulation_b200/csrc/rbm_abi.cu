@@ -1,0 +1,322 @@
+// extern "C" boundary of librbm_b200.so (declared in include/rbm_b200.h) and the host-side model analysis.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "rbm_internal.h"
+
+namespace rbm {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return RBM_ERR_CUDA;
+}
+
+static int invalid(const std::string& msg) {
+  g_last_error = msg;
+  return RBM_ERR_INVALID;
+}
+
+// ---------------------------------------------------------------------------------------------
+// structure analysis: does the model match the compile-time descriptor of rbm_rnea.cuh?
+// ---------------------------------------------------------------------------------------------
+// Entries produced by quaternion round trips are exact up to ~2e-16; anything within kSnap of the
+// descriptor's 0 / +-1 pattern is treated as the pattern (perturbs tau by <= ~1e-13 relative, four orders
+// below the 1e-9 parity bar; RBM_FLAG_FORCE_GENERIC keeps the unsnapped constants).
+static const double kSnap = 1e-13;
+
+static const int kSeqPerm[6][3] = {{-3, 2, 1}, {1, -3, 2}, {3, 2, -1}, {1, 3, -2}, {-3, 2, 1}, {1, -3, 2}};
+static const int kSeqHinge[6] = {0, 0, 0, 1, 1, 1};
+
+static bool near(double a, double b, double tol = kSnap) { return std::fabs(a - b) <= tol; }
+
+static bool rotation_is_perm(const double* R, const int* perm) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      const int col = std::abs(perm[r]) - 1;
+      const double want = (c == col) ? (perm[r] > 0 ? 1.0 : -1.0) : 0.0;
+      if (!near(R[3 * r + c], want)) return false;
+    }
+  return true;
+}
+
+struct RigidForm {
+  double m, h[3], I[6];
+  bool iso;  // h == 0 and I == J * identity
+};
+
+// G == [[m 1, -[h]x], [[h]x, Ibar]] with Ibar symmetric?
+static bool rigid_form(const double* G, RigidForm* out) {
+  double scale = 0.0;
+  for (int i = 0; i < 36; ++i) scale = std::fmax(scale, std::fabs(G[i]));
+  const double tol = 1e-12 * std::fmax(scale, 1e-300);
+  const double m = G[0];
+  auto g = [&](int r, int c) { return G[6 * r + c]; };
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      if (!near(g(r, c), r == c ? m : 0.0, tol)) return false;
+  const double hx = g(5, 1), hy = g(3, 2), hz = g(4, 0);
+  const double hxm[3][3] = {{0, -hz, hy}, {hz, 0, -hx}, {-hy, hx, 0}};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      if (!near(g(3 + r, c), hxm[r][c], tol)) return false;
+      if (!near(g(r, 3 + c), -hxm[r][c], tol)) return false;
+      if (!near(g(3 + r, 3 + c), g(3 + c, 3 + r), tol)) return false;
+    }
+  out->m = m;
+  out->h[0] = hx; out->h[1] = hy; out->h[2] = hz;
+  out->I[0] = g(3, 3); out->I[1] = g(4, 4); out->I[2] = g(5, 5);
+  out->I[3] = g(3, 4); out->I[4] = g(4, 5); out->I[5] = g(5, 3);
+  out->iso = near(hx, 0, tol) && near(hy, 0, tol) && near(hz, 0, tol) && near(out->I[0], out->I[1], tol) && near(out->I[0], out->I[2], tol) &&
+             near(out->I[3], 0, tol) && near(out->I[4], 0, tol) && near(out->I[5], 0, tol);
+  return true;
+}
+
+static int detect_path(int nj, const double* hposes_Rt, const double* simats, const double* uscrews, const double* twist_0,
+                       const double* dtwist_0, const double* wrench_tip, const double* pose_tip, FastParams<double>* fp) {
+  if (nj != 6) return PATH_GENERIC;
+  for (int k = 0; k < 6; ++k)
+    if (twist_0[k] != 0.0 || (wrench_tip && wrench_tip[k] != 0.0)) return PATH_GENERIC;
+  for (int k = 3; k < 6; ++k)
+    if (dtwist_0[k] != 0.0) return PATH_GENERIC;
+  if (pose_tip) {
+    static const int ident[3] = {1, 2, 3};
+    if (!rotation_is_perm(pose_tip, ident)) return PATH_GENERIC;
+    for (int k = 9; k < 12; ++k)
+      if (!near(pose_tip[k], 0.0)) return PATH_GENERIC;
+  }
+  bool all_iso15 = true;
+  for (int i = 0; i < 6; ++i) {
+    const double* S = uscrews + 6 * i;
+    for (int k = 0; k < 6; ++k) {
+      const double want = (k == (kSeqHinge[i] ? 5 : 2)) ? 1.0 : 0.0;
+      if (!near(S[k], want)) return PATH_GENERIC;
+    }
+    const double* H = hposes_Rt + 12 * (i + 1);
+    if (!rotation_is_perm(H, kSeqPerm[i])) return PATH_GENERIC;
+    for (int k = 9; k < 12; ++k)
+      if (!near(H[k], 0.0)) return PATH_GENERIC;
+    RigidForm rf;
+    if (!rigid_form(simats + 36 * (i + 1), &rf)) return PATH_GENERIC;
+    fp->mass[i] = rf.m;
+    for (int k = 0; k < 3; ++k) { fp->h[i][k] = rf.h[k]; fp->tm[i][k] = 0.0; }
+    for (int k = 0; k < 6; ++k) fp->I[i][k] = rf.I[k];
+    if (i < 5 && !rf.iso) all_iso15 = false;
+  }
+  for (int k = 0; k < 3; ++k) fp->g[k] = dtwist_0[k];
+  return all_iso15 ? PATH_SEQ_ISO : PATH_SEQ_RIGID;
+}
+
+template <class T>
+static void convert_fast(const FastParams<double>& a, FastParams<T>* b) {
+  const double* src = reinterpret_cast<const double*>(&a);
+  T* dst = reinterpret_cast<T*>(b);
+  for (size_t i = 0; i < sizeof(FastParams<double>) / sizeof(double); ++i) dst[i] = (T)src[i];
+}
+
+}  // namespace rbm
+
+// ---- host end-to-end path ---------------------------------------------------------------------
+namespace rbm {
+template <class T>
+int rnea_host(const rbm_model* m, const T* traj_host, T* tau_host, int64_t n, int64_t chunk) {
+  if (!m) return invalid("rbm_rnea_host: model is NULL");
+  if (n < 0) return invalid("rbm_rnea_host: n < 0");
+  if (n == 0) return RBM_OK;
+  if (!traj_host || !tau_host) return invalid("rbm_rnea_host: NULL buffer");
+  const int nj = m->nj;
+  if (chunk <= 0) chunk = 1 << 18;
+  if (chunk > n) chunk = n;
+  RBM_CUDA_TRY(cudaSetDevice(m->device));
+  std::lock_guard<std::mutex> lock(m->pipe_mu);
+  constexpr int kSlots = rbm_model::kPipeSlots;
+  const size_t in_bytes = sizeof(T) * chunk * 3 * nj, out_bytes = sizeof(T) * chunk * nj;
+  for (int k = 0; k < kSlots; ++k)
+    if (!m->pipe_st[k]) RBM_CUDA_TRY(cudaStreamCreateWithFlags(&m->pipe_st[k], cudaStreamNonBlocking));
+  if (in_bytes > m->pipe_in_bytes || out_bytes > m->pipe_out_bytes) {
+    for (int k = 0; k < kSlots; ++k) {
+      RBM_CUDA_TRY(cudaStreamSynchronize(m->pipe_st[k]));
+      if (m->pipe_in[k]) cudaFree(m->pipe_in[k]);
+      if (m->pipe_out[k]) cudaFree(m->pipe_out[k]);
+      m->pipe_in[k] = m->pipe_out[k] = nullptr;
+    }
+    m->pipe_in_bytes = m->pipe_out_bytes = 0;
+    for (int k = 0; k < kSlots; ++k) {
+      RBM_CUDA_TRY(cudaMalloc(&m->pipe_in[k], in_bytes));
+      RBM_CUDA_TRY(cudaMalloc(&m->pipe_out[k], out_bytes));
+    }
+    m->pipe_in_bytes = in_bytes;
+    m->pipe_out_bytes = out_bytes;
+  }
+  int slot = 0;
+  for (int64_t s0 = 0; s0 < n; s0 += chunk, slot = (slot + 1) % kSlots) {
+    const int64_t cnt = (n - s0 < chunk) ? (n - s0) : chunk;
+    cudaStream_t st = m->pipe_st[slot];
+    T* d_in = static_cast<T*>(m->pipe_in[slot]);
+    T* d_out = static_cast<T*>(m->pipe_out[slot]);
+    // stream order makes the slot safe to reuse: its previous D2H precedes this H2D on the same stream
+    RBM_CUDA_TRY(cudaMemcpyAsync(d_in, traj_host + s0 * 3 * nj, sizeof(T) * cnt * 3 * nj, cudaMemcpyHostToDevice, st));
+    int rc = launch_rnea_aos<T>(m, d_in, d_out, cnt, st);
+    if (rc != RBM_OK) return rc;
+    RBM_CUDA_TRY(cudaMemcpyAsync(tau_host + s0 * nj, d_out, sizeof(T) * cnt * nj, cudaMemcpyDeviceToHost, st));
+  }
+  for (int k = 0; k < kSlots; ++k) RBM_CUDA_TRY(cudaStreamSynchronize(m->pipe_st[k]));
+  return RBM_OK;
+}
+}  // namespace rbm
+
+
+using namespace rbm;
+
+extern "C" {
+
+const char* rbm_version(void) { return "rbm_b200 0.1 (sm_100a)"; }
+const char* rbm_last_error_string(void) { return g_last_error.c_str(); }
+
+int rbm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int rbm_model_create(int nj, const double* hposes_Rt, const double* simats, const double* uscrews, const double* twist_0,
+                     const double* dtwist_0, const double* wrench_tip, const double* pose_tip_Rt, const double* pose_sen_Rt,
+                     unsigned flags, int device, rbm_model** out) {
+  if (!out) return invalid("rbm_model_create: out is NULL");
+  *out = nullptr;
+  if (nj < 1) return invalid("rbm_model_create: nj must be >= 1");
+  if (nj > RBM_MAX_JOINTS) {
+    set_error("rbm_model_create: nj exceeds RBM_MAX_JOINTS (16)");
+    return RBM_ERR_UNSUPPORTED;
+  }
+  if (!hposes_Rt || !simats || !uscrews || !twist_0 || !dtwist_0) return invalid("rbm_model_create: NULL constant array");
+  const int np = generic_param_count(nj);
+  for (int i = 0; i < (nj + 1) * 12; ++i)
+    if (!std::isfinite(hposes_Rt[i])) return invalid("rbm_model_create: non-finite home pose");
+  for (int i = 0; i < (nj + 1) * 36; ++i)
+    if (!std::isfinite(simats[i])) return invalid("rbm_model_create: non-finite spatial inertia");
+  for (int i = 0; i < nj * 6; ++i)
+    if (!std::isfinite(uscrews[i])) return invalid("rbm_model_create: non-finite screw");
+
+  rbm_model* m = new (std::nothrow) rbm_model();
+  if (!m) return invalid("rbm_model_create: out of host memory");
+  m->nj = nj;
+  m->device = device;
+  m->gp64.assign(np, 0.0);
+  double* g = m->gp64.data();
+  static const double ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+  std::memcpy(g + GP_V0, twist_0, 6 * sizeof(double));
+  std::memcpy(g + GP_DV0, dtwist_0, 6 * sizeof(double));
+  if (wrench_tip) std::memcpy(g + GP_FTIP, wrench_tip, 6 * sizeof(double));
+  std::memcpy(g + GP_TIPR, pose_tip_Rt ? pose_tip_Rt : ident, 12 * sizeof(double));
+  std::memcpy(g + GP_SENR, pose_sen_Rt ? pose_sen_Rt : ident, 12 * sizeof(double));
+  for (int i = 0; i < nj; ++i) {
+    double* J = g + GP_HEAD + GJ_STRIDE * i;
+    std::memcpy(J + GJ_HR, hposes_Rt + 12 * (i + 1), 12 * sizeof(double));
+    std::memcpy(J + GJ_S, uscrews + 6 * i, 6 * sizeof(double));
+    const double* w = uscrews + 6 * i + 3;
+    const double wn = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    J[GJ_WN] = wn;
+    for (int k = 0; k < 3; ++k) J[GJ_AXIS + k] = wn > 0.0 ? w[k] / wn : 0.0;
+    std::memcpy(J + GJ_G, simats + 36 * (i + 1), 36 * sizeof(double));
+  }
+  m->gp32.resize(np);
+  for (int i = 0; i < np; ++i) m->gp32[i] = (float)g[i];
+
+  std::memset(&m->fp64, 0, sizeof(m->fp64));
+  m->path = PATH_GENERIC;
+  if (!(flags & RBM_FLAG_FORCE_GENERIC))
+    m->path = detect_path(nj, hposes_Rt, simats, uscrews, twist_0, dtwist_0, wrench_tip, pose_tip_Rt, &m->fp64);
+  std::memcpy(m->fp64.senR, g + GP_SENR, 9 * sizeof(double));
+  std::memcpy(m->fp64.sent, g + GP_SENT, 3 * sizeof(double));
+  convert_fast(m->fp64, &m->fp32);
+
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_gp64, np * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_gp32, np * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_gp64, m->gp64.data(), np * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_gp32, m->gp32.data(), np * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    int rc = cuda_fail(e, "rbm_model_create (device allocation / upload)");
+    cudaGetLastError();
+    rbm_model_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return RBM_OK;
+}
+
+void rbm_model_destroy(rbm_model* m) {
+  if (!m) return;
+  for (int k = 0; k < rbm_model::kPipeSlots; ++k) {
+    if (m->pipe_st[k]) cudaStreamDestroy(m->pipe_st[k]);
+    if (m->pipe_in[k]) cudaFree(m->pipe_in[k]);
+    if (m->pipe_out[k]) cudaFree(m->pipe_out[k]);
+  }
+  if (m->d_gp64) cudaFree(m->d_gp64);
+  if (m->d_gp32) cudaFree(m->d_gp32);
+  delete m;
+}
+
+int rbm_model_num_joints(const rbm_model* m) { return m ? m->nj : RBM_ERR_INVALID; }
+int rbm_model_kernel_path(const rbm_model* m) { return m ? m->path : RBM_ERR_INVALID; }
+
+#define RBM_CHECK_BATCH(name)                                                         \
+  if (!m) return invalid(name ": model is NULL");                                    \
+  if (n < 0) return invalid(name ": n < 0");                                         \
+  if (n == 0) return RBM_OK;
+
+int rbm_rnea_f64(const rbm_model* m, const double* q, const double* qd, const double* qdd, double* tau, double* twist_last,
+                 double* dtwist_last, int64_t n, int64_t ld, void* stream) {
+  RBM_CHECK_BATCH("rbm_rnea_f64")
+  if (!q || !qd || !qdd || !tau) return invalid("rbm_rnea_f64: NULL batch pointer");
+  if (ld < n) return invalid("rbm_rnea_f64: ld < n");
+  if ((twist_last == nullptr) != (dtwist_last == nullptr)) return invalid("rbm_rnea_f64: twist_last and dtwist_last go together");
+  return launch_rnea_soa<double>(m, q, qd, qdd, tau, twist_last, dtwist_last, n, ld, (cudaStream_t)stream);
+}
+
+int rbm_rnea_f32(const rbm_model* m, const float* q, const float* qd, const float* qdd, float* tau, float* twist_last,
+                 float* dtwist_last, int64_t n, int64_t ld, void* stream) {
+  RBM_CHECK_BATCH("rbm_rnea_f32")
+  if (!q || !qd || !qdd || !tau) return invalid("rbm_rnea_f32: NULL batch pointer");
+  if (ld < n) return invalid("rbm_rnea_f32: ld < n");
+  if ((twist_last == nullptr) != (dtwist_last == nullptr)) return invalid("rbm_rnea_f32: twist_last and dtwist_last go together");
+  return launch_rnea_soa<float>(m, q, qd, qdd, tau, twist_last, dtwist_last, n, ld, (cudaStream_t)stream);
+}
+
+int rbm_rnea_aos_f64(const rbm_model* m, const double* traj, double* tau, int64_t n, void* stream) {
+  RBM_CHECK_BATCH("rbm_rnea_aos_f64")
+  if (!traj || !tau) return invalid("rbm_rnea_aos_f64: NULL batch pointer");
+  return launch_rnea_aos<double>(m, traj, tau, n, (cudaStream_t)stream);
+}
+
+int rbm_rnea_aos_f32(const rbm_model* m, const float* traj, float* tau, int64_t n, void* stream) {
+  RBM_CHECK_BATCH("rbm_rnea_aos_f32")
+  if (!traj || !tau) return invalid("rbm_rnea_aos_f32: NULL batch pointer");
+  return launch_rnea_aos<float>(m, traj, tau, n, (cudaStream_t)stream);
+}
+
+int rbm_rnea_full_f64(const rbm_model* m, const double* traj, double* tau, double* poses, double* twists, double* dtwists, int64_t n,
+                      void* stream) {
+  RBM_CHECK_BATCH("rbm_rnea_full_f64")
+  if (!traj || !tau) return invalid("rbm_rnea_full_f64: NULL batch pointer");
+  if ((twists == nullptr) != (dtwists == nullptr)) return invalid("rbm_rnea_full_f64: twists and dtwists go together");
+  return launch_rnea_full<double>(m, traj, tau, poses, twists, dtwists, n, (cudaStream_t)stream);
+}
+
+int rbm_rnea_host_f64(const rbm_model* m, const double* traj_host, double* tau_host, int64_t n, int64_t chunk) {
+  return rnea_host<double>(m, traj_host, tau_host, n, chunk);
+}
+int rbm_rnea_host_f32(const rbm_model* m, const float* traj_host, float* tau_host, int64_t n, int64_t chunk) {
+  return rnea_host<float>(m, traj_host, tau_host, n, chunk);
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+// Batched inverse-dynamics kernels and their launchers (sm_100a).
+//
+// One sample per thread; consecutive threads own consecutive samples, so every SoA stream
+// (q_j, qd_j, qdd_j, tau_j) is read / written as fully coalesced 128-byte lines and nothing is
+// re-read: HBM traffic == algorithmic traffic == 24 * sizeof(T) bytes per sample.
+#include "rbm_internal.h"
+#include "rbm_rnea.cuh"
+
+namespace rbm {
+
+constexpr int kBlock = 128;
+
+// ---------------------------------------------------------------------------------------------
+// fast path, SoA
+// ---------------------------------------------------------------------------------------------
+template <class T, class D, bool OUT_TWIST>
+__global__ void __launch_bounds__(kBlock) k_rnea_fast_soa(const __grid_constant__ FastParams<T> P, const T* __restrict__ q,
+                                                          const T* __restrict__ qd, const T* __restrict__ qdd, T* __restrict__ tau,
+                                                          T* __restrict__ Vout, T* __restrict__ dVout, int64_t n, int64_t ld) {
+  const int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (s >= n) return;
+  T rq[6], rqd[6], rqdd[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    rq[j] = __ldg(q + j * ld + s);
+    rqd[j] = __ldg(qd + j * ld + s);
+    rqdd[j] = __ldg(qdd + j * ld + s);
+  }
+  FastResult<T> r;
+  fast_rnea<T, D, true>(P, rq, rqd, rqdd, r);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) tau[j * ld + s] = r.tau[j];
+  if constexpr (OUT_TWIST) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      Vout[j * ld + s] = r.v[j];
+      Vout[(j + 3) * ld + s] = r.w[j];
+      dVout[j * ld + s] = r.a[j];
+      dVout[(j + 3) * ld + s] = r.l[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic path, SoA.  Parameters are staged once per block into shared memory.
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void stage_params(const T* __restrict__ gp, int count, T* sp) {
+  for (int i = threadIdx.x; i < count; i += blockDim.x) sp[i] = gp[i];
+  __syncthreads();
+}
+
+template <class T, int NJ>
+__global__ void __launch_bounds__(kBlock) k_rnea_generic_soa(const T* __restrict__ gp, int nj, int nparams, const T* __restrict__ q,
+                                                             const T* __restrict__ qd, const T* __restrict__ qdd, T* __restrict__ tau,
+                                                             T* __restrict__ Vout, T* __restrict__ dVout, int64_t n, int64_t ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sp = reinterpret_cast<T*>(smem_raw);
+  stage_params(gp, nparams, sp);
+  const int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (s >= n) return;
+  constexpr int MAXJ = NJ > 0 ? NJ : RBM_MAX_JOINTS;
+  T rq[MAXJ], rqd[MAXJ], rqdd[MAXJ], rtau[MAXJ];
+  const int njr = NJ > 0 ? NJ : nj;
+#pragma unroll
+  for (int j = 0; j < njr; ++j) {
+    rq[j] = __ldg(q + j * ld + s);
+    rqd[j] = __ldg(qd + j * ld + s);
+    rqdd[j] = __ldg(qdd + j * ld + s);
+  }
+  T V[6], dV[6];
+  generic_rnea<T, NJ>(sp, nj, rq, rqd, rqdd, rtau, nullptr, nullptr, nullptr, V, dV);
+#pragma unroll
+  for (int j = 0; j < njr; ++j) tau[j * ld + s] = rtau[j];
+  if (Vout) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      Vout[j * ld + s] = V[j];
+      dVout[j * ld + s] = dV[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// AoS kernels: traj [n][3][nj] -> tau [n][nj].  A block's tile of kBlock samples is one contiguous span
+// in both arrays; it is moved with coalesced accesses and transposed through shared memory.
+// ---------------------------------------------------------------------------------------------
+template <class T, class D>
+__global__ void __launch_bounds__(kBlock) k_rnea_fast_aos(const __grid_constant__ FastParams<T> P, const T* __restrict__ traj,
+                                                          T* __restrict__ tau, int64_t n) {
+  __shared__ T tile[kBlock * 18];
+  const int64_t s0 = (int64_t)blockIdx.x * kBlock;
+  const int cnt = (int)min((int64_t)kBlock, n - s0);
+  const T* src = traj + s0 * 18;
+  for (int i = threadIdx.x; i < cnt * 18; i += kBlock) tile[i] = __ldg(src + i);
+  __syncthreads();
+  FastResult<T> r;
+  if (threadIdx.x < cnt) {
+    const T* my = tile + threadIdx.x * 18;
+    T rq[6], rqd[6], rqdd[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { rq[j] = my[j]; rqd[j] = my[6 + j]; rqdd[j] = my[12 + j]; }
+    fast_rnea<T, D, true>(P, rq, rqd, rqdd, r);
+  }
+  __syncthreads();
+  if (threadIdx.x < cnt) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) tile[threadIdx.x * 6 + j] = r.tau[j];
+  }
+  __syncthreads();
+  T* dst = tau + s0 * 6;
+  for (int i = threadIdx.x; i < cnt * 6; i += kBlock) dst[i] = tile[i];
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_rnea_generic_aos(const T* __restrict__ gp, int nj, int nparams, const T* __restrict__ traj,
+                                                             T* __restrict__ tau, T* __restrict__ poses, T* __restrict__ twists,
+                                                             T* __restrict__ dtwists, int64_t n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sp = reinterpret_cast<T*>(smem_raw);
+  stage_params(gp, nparams, sp);
+  const int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (s >= n) return;
+  T rq[RBM_MAX_JOINTS], rqd[RBM_MAX_JOINTS], rqdd[RBM_MAX_JOINTS], rtau[RBM_MAX_JOINTS];
+  const T* my = traj + s * 3 * nj;
+  for (int j = 0; j < nj; ++j) { rq[j] = my[j]; rqd[j] = my[nj + j]; rqdd[j] = my[2 * nj + j]; }
+  generic_rnea<T, 0>(sp, nj, rq, rqd, rqdd, rtau, poses ? poses + s * nj * 12 : nullptr, twists ? twists + s * (nj + 1) * 6 : nullptr,
+                     dtwists ? dtwists + s * (nj + 1) * 6 : nullptr, nullptr, nullptr);
+  for (int j = 0; j < nj; ++j) tau[s * nj + j] = rtau[j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+template <class T>
+int launch_rnea_soa(const rbm_model* m, const T* q, const T* qd, const T* qdd, T* tau, T* V, T* dV, int64_t n, int64_t ld, cudaStream_t st) {
+  if (n == 0) return RBM_OK;
+  const unsigned grid = grid_for(n);
+  const bool tw = (V != nullptr);
+  if (m->path == PATH_SEQ_ISO) {
+    if (tw) k_rnea_fast_soa<T, SeqIso, true><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld);
+    else k_rnea_fast_soa<T, SeqIso, false><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld);
+  } else if (m->path == PATH_SEQ_RIGID) {
+    if (tw) k_rnea_fast_soa<T, SeqRigid, true><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld);
+    else k_rnea_fast_soa<T, SeqRigid, false><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld);
+  } else {
+    const int np = generic_param_count(m->nj);
+    const size_t sm = sizeof(T) * np;
+    if (m->nj == 6) k_rnea_generic_soa<T, 6><<<grid, kBlock, sm, st>>>(ModelView<T>::generic(m), m->nj, np, q, qd, qdd, tau, V, dV, n, ld);
+    else k_rnea_generic_soa<T, 0><<<grid, kBlock, sm, st>>>(ModelView<T>::generic(m), m->nj, np, q, qd, qdd, tau, V, dV, n, ld);
+  }
+  RBM_CUDA_TRY(cudaGetLastError());
+  return RBM_OK;
+}
+
+template <class T>
+int launch_rnea_aos(const rbm_model* m, const T* traj, T* tau, int64_t n, cudaStream_t st) {
+  if (n == 0) return RBM_OK;
+  const unsigned grid = grid_for(n);
+  if (m->path == PATH_SEQ_ISO) {
+    k_rnea_fast_aos<T, SeqIso><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), traj, tau, n);
+  } else if (m->path == PATH_SEQ_RIGID) {
+    k_rnea_fast_aos<T, SeqRigid><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), traj, tau, n);
+  } else {
+    const int np = generic_param_count(m->nj);
+    k_rnea_generic_aos<T><<<grid, kBlock, sizeof(T) * np, st>>>(ModelView<T>::generic(m), m->nj, np, traj, tau, nullptr, nullptr, nullptr, n);
+  }
+  RBM_CUDA_TRY(cudaGetLastError());
+  return RBM_OK;
+}
+
+template <class T>
+int launch_rnea_full(const rbm_model* m, const T* traj, T* tau, T* poses, T* twists, T* dtwists, int64_t n, cudaStream_t st) {
+  if (n == 0) return RBM_OK;
+  const int np = generic_param_count(m->nj);
+  k_rnea_generic_aos<T><<<grid_for(n), kBlock, sizeof(T) * np, st>>>(ModelView<T>::generic(m), m->nj, np, traj, tau, poses, twists, dtwists, n);
+  RBM_CUDA_TRY(cudaGetLastError());
+  return RBM_OK;
+}
+
+template int launch_rnea_soa<double>(const rbm_model*, const double*, const double*, const double*, double*, double*, double*, int64_t, int64_t, cudaStream_t);
+template int launch_rnea_soa<float>(const rbm_model*, const float*, const float*, const float*, float*, float*, float*, int64_t, int64_t, cudaStream_t);
+template int launch_rnea_aos<double>(const rbm_model*, const double*, double*, int64_t, cudaStream_t);
+template int launch_rnea_aos<float>(const rbm_model*, const float*, float*, int64_t, cudaStream_t);
+template int launch_rnea_full<double>(const rbm_model*, const double*, double*, double*, double*, double*, int64_t, cudaStream_t);
+
+}  // namespace rbm

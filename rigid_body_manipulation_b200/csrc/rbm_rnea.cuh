@@ -1,0 +1,393 @@
+// Device-side recursive Newton-Euler inverse dynamics (reference dynamics/dynamics.py:109-157,
+// Modern Robotics Eq. 8.50-8.54, twists in [v; w] order).
+//
+//   fast path   : fast_rnea<T, Desc>()   -- structure fixed at compile time (rbm_typed.cuh), one
+//                 sample per thread, whole chain state in registers.
+//   generic path: generic_rnea<T, NJ>()  -- any model, parameters read from shared memory.
+#pragma once
+#include "rbm_model.cuh"
+#include "rbm_typed.cuh"
+
+namespace rbm {
+
+// =================================================================================================
+// Structure descriptors
+// =================================================================================================
+enum JointKind : int { JOINT_PZ = 0, JOINT_RZ = 1 };          // prismatic along +z / revolute about +z
+enum InertiaKind : int { INERTIA_ISO = 0, INERTIA_RIGID = 1 }; // diag(m,m,m,I,I,I) / general rigid body
+
+template <int JK, class Perm, bool HasT, int IK>
+struct LinkD {
+  static constexpr int jk = JK;
+  using perm = Perm;               // home rotation hposes_body_parent[i+1].R as a signed permutation
+  static constexpr bool has_t = HasT;  // home translation non-zero?
+  static constexpr int ik = IK;
+};
+
+// The reference's manipulator (xml_models/manipulators/sequential.xml:13-39): x/y/z gantry then a
+// roll/pitch/yaw wrist, every joint about its own +z, body eulers single-axis +-90 deg, all body and
+// joint positions zero, links 1-5 an 8 kg isotropic block, link 6 the block plus attachment + object
+// (core/simulate.py:129-137).  Home rotations below are hposes_lj_kj[1..6].R (core/simulate.py:140-146).
+template <int IK15>
+struct SequentialDesc {
+  using L0 = LinkD<JOINT_PZ, SPerm<-3, 2, 1>, false, IK15>;
+  using L1 = LinkD<JOINT_PZ, SPerm<1, -3, 2>, false, IK15>;
+  using L2 = LinkD<JOINT_PZ, SPerm<3, 2, -1>, false, IK15>;
+  using L3 = LinkD<JOINT_RZ, SPerm<1, 3, -2>, false, IK15>;
+  using L4 = LinkD<JOINT_RZ, SPerm<-3, 2, 1>, false, IK15>;
+  using L5 = LinkD<JOINT_RZ, SPerm<1, -3, 2>, false, INERTIA_RIGID>;
+};
+using SeqIso = SequentialDesc<INERTIA_ISO>;
+using SeqRigid = SequentialDesc<INERTIA_RIGID>;
+
+// =================================================================================================
+// Fast path
+// =================================================================================================
+template <class VV, class WW, class AA, class LL, class PP, class BF, class BM>
+struct LinkOut {
+  VV v;   // linear part of the twist V_i
+  WW w;   // angular part
+  AA a;   // linear part of dV_i
+  LL l;   // angular part
+  PP p;   // translation of T_i = T_{i,i-1}
+  BF bf;  // body wrench  G_i dV_i - ad(V_i)^T G_i V_i, force part
+  BM bm;  // moment part
+};
+template <class VV, class WW, class AA, class LL, class PP, class BF, class BM>
+RBM_HD LinkOut<VV, WW, AA, LL, PP, BF, BM> mk_link(VV v, WW w, AA a, LL l, PP p, BF bf, BM bm) {
+  return {v, w, a, l, p, bf, bm};
+}
+
+// R_i x  with  R_i = Rz(-q) * P  (revolute)  or  P  (prismatic)
+template <class L, class T, class V>
+RBM_HD auto link_rot(T c, T s, const V& x) {
+  auto y = sp_apply<typename L::perm>(x);
+  if constexpr (L::jk == JOINT_RZ) return rotz_neg(c, s, y);
+  else return y;
+}
+// R_i^T x
+template <class L, class T, class V>
+RBM_HD auto link_rot_T(T c, T s, const V& x) {
+  if constexpr (L::jk == JOINT_RZ) return sp_apply_T<typename L::perm>(rotz_pos(c, s, x));
+  else return sp_apply_T<typename L::perm>(x);
+}
+
+// b_i = G_i dV_i - ad(V_i)^T G_i V_i  (the two inertia terms of Eq. 8.53)
+template <class L, int I, class T, class VV, class WW, class AA, class LL, class PP>
+RBM_HD auto fwd_wrench(const FastParams<T>& P, const VV& v, const WW& w, const AA& a, const LL& l, const PP& p) {
+  const T m = P.mass[I];
+  if constexpr (L::ik == INERTIA_ISO) {
+    // G = diag(m,m,m,J,J,J):  b = [ m (a + w x v) ;  J l ]   (w x Jw = 0, v x mv = 0)
+    auto bf = scale(m, a + cross(w, v));
+    auto bm = scale(P.I[I][0], l);
+    return mk_link(v, w, a, l, p, bf, bm);
+  } else {
+    // G = [[m 1, -[h]x], [[h]x, Ibar]]
+    auto h = ld3(P.h[I]);
+    auto pl = scale(m, v) + cross(w, h);              // linear momentum
+    auto pa = cross(h, v) + sym3_mul(P.I[I], w);      // angular momentum about the frame origin
+    auto bf = scale(m, a) + cross(l, h) + cross(w, pl);
+    auto bm = cross(h, a) + sym3_mul(P.I[I], l) + cross(v, pl) + cross(w, pa);
+    return mk_link(v, w, a, l, p, bf, bm);
+  }
+}
+
+// One forward step (Eq. 8.50-8.52) plus the link's body wrench.
+template <class L, int I, class T, class VV, class WW, class AA, class LL>
+RBM_HD auto fwd_link(const FastParams<T>& P, T q, T qd, T qdd, T c, T s, const VV& vp, const WW& wp, const AA& ap, const LL& lp) {
+  // translation of T_i = exp(-S q) * M_i
+  auto tm = [&] {
+    if constexpr (L::has_t) return ld3(P.tm[I]);
+    else return Z3{};
+  }();
+  auto p = [&] {
+    if constexpr (L::jk == JOINT_RZ) {
+      if constexpr (L::has_t) return rotz_neg(c, s, tm);
+      else return Z3{};
+    } else {
+      return tm + mk3(Z{}, Z{}, -q);
+    }
+  }();
+  auto Rw = link_rot<L>(c, s, wp);
+  auto Rl = link_rot<L>(c, s, lp);
+  auto Rv = link_rot<L>(c, s, vp) + cross(p, Rw);   // Ad(T) acting on [v; w]
+  auto Ra = link_rot<L>(c, s, ap) + cross(p, Rl);
+  if constexpr (L::jk == JOINT_RZ) {
+    auto w = Rw + mk3(Z{}, Z{}, qd);                                  // Eq. 8.51
+    auto v = Rv;
+    auto l = Rl + scale(qd, cross_e3(w)) + mk3(Z{}, Z{}, qdd);        // Eq. 8.52: ad(V) S qd + S qdd
+    auto a = Ra + scale(qd, cross_e3(v));
+    return fwd_wrench<L, I>(P, v, w, a, l, p);
+  } else {
+    auto w = Rw;
+    auto v = Rv + mk3(Z{}, Z{}, qd);
+    auto l = Rl;
+    auto a = Ra + scale(qd, cross_e3(w)) + mk3(Z{}, Z{}, qdd);
+    return fwd_wrench<L, I>(P, v, w, a, l, p);
+  }
+}
+
+// One backward step (Eq. 8.53): F_i = Ad(T_{i+1})^T F_{i+1} + b_i, where (c, s, p) belong to link i+1.
+template <class Lnext, class T, class PP, class FF, class MM, class BF, class BM>
+RBM_HD auto bwd_link(T c, T s, const PP& p, const FF& f, const MM& mo, const BF& bf, const BM& bm) {
+  auto fo = link_rot_T<Lnext>(c, s, f) + bf;
+  auto mo2 = link_rot_T<Lnext>(c, s, mo - cross(p, f)) + bm;
+  struct R { decltype(fo) f; decltype(mo2) m; };
+  return R{fo, mo2};
+}
+
+template <class T>
+struct FastResult {
+  T tau[6];
+  T v[3], w[3], a[3], l[3];  // twist and twist rate of the last link (V_6, dV_6)
+};
+
+template <class T> RBM_HD void sincos_t(T x, T* s, T* c);
+template <> RBM_HD void sincos_t<double>(double x, double* s, double* c) { sincos(x, s, c); }
+template <> RBM_HD void sincos_t<float>(float x, float* s, float* c) { sincosf(x, s, c); }
+
+// Full RNEA for one sample.  WANT_TAU = false leaves the backward sweep out (regressor kernels).
+template <class T, class D, bool WANT_TAU>
+RBM_HD void fast_rnea(const FastParams<T>& P, const T (&q)[6], const T (&qd)[6], const T (&qdd)[6], FastResult<T>& out) {
+  T c[6], s[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { c[i] = T(1); s[i] = T(0); }
+  if constexpr (D::L0::jk == JOINT_RZ) sincos_t(q[0], &s[0], &c[0]);
+  if constexpr (D::L1::jk == JOINT_RZ) sincos_t(q[1], &s[1], &c[1]);
+  if constexpr (D::L2::jk == JOINT_RZ) sincos_t(q[2], &s[2], &c[2]);
+  if constexpr (D::L3::jk == JOINT_RZ) sincos_t(q[3], &s[3], &c[3]);
+  if constexpr (D::L4::jk == JOINT_RZ) sincos_t(q[4], &s[4], &c[4]);
+  if constexpr (D::L5::jk == JOINT_RZ) sincos_t(q[5], &s[5], &c[5]);
+
+  // base: twist_0 = 0, dtwist_0 = [g; 0]  (core/simulate.py:149,154-155)
+  auto v0 = Z3{};
+  auto w0 = Z3{};
+  auto a0 = ld3(P.g);
+  auto l0 = Z3{};
+  auto k0 = fwd_link<typename D::L0, 0>(P, q[0], qd[0], qdd[0], c[0], s[0], v0, w0, a0, l0);
+  auto k1 = fwd_link<typename D::L1, 1>(P, q[1], qd[1], qdd[1], c[1], s[1], k0.v, k0.w, k0.a, k0.l);
+  auto k2 = fwd_link<typename D::L2, 2>(P, q[2], qd[2], qdd[2], c[2], s[2], k1.v, k1.w, k1.a, k1.l);
+  auto k3 = fwd_link<typename D::L3, 3>(P, q[3], qd[3], qdd[3], c[3], s[3], k2.v, k2.w, k2.a, k2.l);
+  auto k4 = fwd_link<typename D::L4, 4>(P, q[4], qd[4], qdd[4], c[4], s[4], k3.v, k3.w, k3.a, k3.l);
+  auto k5 = fwd_link<typename D::L5, 5>(P, q[5], qd[5], qdd[5], c[5], s[5], k4.v, k4.w, k4.a, k4.l);
+
+  out.v[0] = to_scalar<T>(k5.v.x); out.v[1] = to_scalar<T>(k5.v.y); out.v[2] = to_scalar<T>(k5.v.z);
+  out.w[0] = to_scalar<T>(k5.w.x); out.w[1] = to_scalar<T>(k5.w.y); out.w[2] = to_scalar<T>(k5.w.z);
+  out.a[0] = to_scalar<T>(k5.a.x); out.a[1] = to_scalar<T>(k5.a.y); out.a[2] = to_scalar<T>(k5.a.z);
+  out.l[0] = to_scalar<T>(k5.l.x); out.l[1] = to_scalar<T>(k5.l.y); out.l[2] = to_scalar<T>(k5.l.z);
+
+  if constexpr (WANT_TAU) {
+    // backward sweep; wrench_tip = 0 and pose_tip_ee = I (dynamics/dynamics.py:116-117) => F_6 = b_6
+    auto pick = [](auto Ld, const auto& f, const auto& m) {
+      using L = decltype(Ld);
+      if constexpr (L::jk == JOINT_RZ) return to_scalar<T>(m.z);
+      else return to_scalar<T>(f.z);
+    };
+    auto f5 = k5.bf;
+    auto m5 = k5.bm;
+    out.tau[5] = pick(typename D::L5{}, f5, m5);
+    auto F4 = bwd_link<typename D::L5>(c[5], s[5], k5.p, f5, m5, k4.bf, k4.bm);
+    out.tau[4] = pick(typename D::L4{}, F4.f, F4.m);
+    auto F3 = bwd_link<typename D::L4>(c[4], s[4], k4.p, F4.f, F4.m, k3.bf, k3.bm);
+    out.tau[3] = pick(typename D::L3{}, F3.f, F3.m);
+    auto F2 = bwd_link<typename D::L3>(c[3], s[3], k3.p, F3.f, F3.m, k2.bf, k2.bm);
+    out.tau[2] = pick(typename D::L2{}, F2.f, F2.m);
+    auto F1 = bwd_link<typename D::L2>(c[2], s[2], k2.p, F2.f, F2.m, k1.bf, k1.bm);
+    out.tau[1] = pick(typename D::L1{}, F1.f, F1.m);
+    auto F0 = bwd_link<typename D::L1>(c[1], s[1], k1.p, F1.f, F1.m, k0.bf, k0.bm);
+    out.tau[0] = pick(typename D::L0{}, F0.f, F0.m);
+  }
+}
+
+// =================================================================================================
+// Generic path (parameters in shared memory, layout in rbm_model.cuh)
+// =================================================================================================
+template <class T> struct G3 { T x, y, z; };
+template <class T> RBM_HD G3<T> g3(const T* p) { return {p[0], p[1], p[2]}; }
+template <class T> RBM_HD G3<T> operator+(G3<T> a, G3<T> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <class T> RBM_HD G3<T> operator-(G3<T> a, G3<T> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <class T> RBM_HD G3<T> operator*(T s, G3<T> a) { return {s * a.x, s * a.y, s * a.z}; }
+template <class T> RBM_HD G3<T> gcross(G3<T> a, G3<T> b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+template <class T> RBM_HD G3<T> mat_vec(const T* R, G3<T> v) {  // row-major 3x3
+  return {R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z};
+}
+template <class T> RBM_HD G3<T> matT_vec(const T* R, G3<T> v) {
+  return {R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z, R[2] * v.x + R[5] * v.y + R[8] * v.z};
+}
+
+template <class T> RBM_HD T abs_t(T x) { return x < T(0) ? -x : x; }
+
+// T_i = SE3.exp(-S q) . M_i  (dynamics.py:126) with liegroups' Rodrigues / left-Jacobian formulas and
+// its isclose(angle, 0) first-order branch (atol 1e-8).  Writes R (row-major 9) and p (3).
+template <class T>
+RBM_HD void joint_transform(const T* J /* per-joint param block */, T q, T* R, T* p) {
+  const T* hR = J + GJ_HR;
+  G3<T> ht = g3(J + GJ_HT);
+  G3<T> rho = (-q) * g3(J + GJ_S);
+  G3<T> ax = g3(J + GJ_AXIS);
+  const T wn = J[GJ_WN];
+  const T theta = -q * wn;   // signed rotation angle about `ax`
+  T E[9], te[3];
+  if (abs_t(theta) <= T(1e-8)) {
+    // R = I + [phi]x ,  J_l = I + 0.5 [phi]x   with phi = -S_w q
+    G3<T> phi = (-q) * g3(J + GJ_S + 3);
+    E[0] = T(1); E[1] = -phi.z; E[2] = phi.y;
+    E[3] = phi.z; E[4] = T(1); E[5] = -phi.x;
+    E[6] = -phi.y; E[7] = phi.x; E[8] = T(1);
+    G3<T> t = rho + T(0.5) * gcross(phi, rho);
+    te[0] = t.x; te[1] = t.y; te[2] = t.z;
+  } else {
+    T s, c;
+    sincos_t(theta, &s, &c);
+    const T oc = T(1) - c;
+    E[0] = c + oc * ax.x * ax.x;        E[1] = oc * ax.x * ax.y - s * ax.z; E[2] = oc * ax.x * ax.z + s * ax.y;
+    E[3] = oc * ax.y * ax.x + s * ax.z; E[4] = c + oc * ax.y * ax.y;        E[5] = oc * ax.y * ax.z - s * ax.x;
+    E[6] = oc * ax.z * ax.x - s * ax.y; E[7] = oc * ax.z * ax.y + s * ax.x; E[8] = c + oc * ax.z * ax.z;
+    // J_l rho = (s/th) rho + (1 - s/th) a (a.rho) + ((1-c)/th) a x rho
+    const T sa = s / theta, ob = oc / theta;
+    const T ar = ax.x * rho.x + ax.y * rho.y + ax.z * rho.z;
+    G3<T> t = sa * rho + ((T(1) - sa) * ar) * ax + ob * gcross(ax, rho);
+    te[0] = t.x; te[1] = t.y; te[2] = t.z;
+  }
+  // R = E hR ; p = E ht + te
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) R[3 * r + cc] = E[3 * r] * hR[cc] + E[3 * r + 1] * hR[3 + cc] + E[3 * r + 2] * hR[6 + cc];
+  }
+  G3<T> pp = mat_vec(E, ht);
+  p[0] = pp.x + te[0]; p[1] = pp.y + te[1]; p[2] = pp.z + te[2];
+}
+
+// Ad(T) [v; w] = [R v + p x (R w); R w]
+template <class T>
+RBM_HD void adjoint_apply(const T* R, G3<T> p, G3<T> v, G3<T> w, G3<T>& vo, G3<T>& wo) {
+  wo = mat_vec(R, w);
+  vo = mat_vec(R, v) + gcross(p, wo);
+}
+// Ad(T)^T [f; m] = [R^T f; R^T (m - p x f)]
+template <class T>
+RBM_HD void adjointT_apply(const T* R, G3<T> p, G3<T> f, G3<T> m, G3<T>& fo, G3<T>& mo) {
+  fo = matT_vec(R, f);
+  mo = matT_vec(R, m - gcross(p, f));
+}
+
+// Generic RNEA for one sample.  NJ > 0: compile-time joint count (loops unroll, state in registers);
+// NJ == 0: run-time count (per-link state lives in local memory).  The body wrench
+// b_i = G_i dV_i - ad(V_i)^T G_i V_i is formed during the forward sweep so that only (R_i, p_i, b_i)
+// survive until the backward sweep.  Optional full-state outputs mirror the reference's return value
+// (tau, poses, twists, dtwists) for the scalar drop-in API.
+template <class T, int NJ>
+__device__ __forceinline__ void generic_rnea(const T* __restrict__ sp, int nj_rt, const T* q, const T* qd, const T* qdd, T* tau,
+                                             T* poses /* [nj][12] or null */, T* twists /* [nj+1][6] or null */, T* dtwists /* idem */,
+                                             T* Vlast /* [6] or null */, T* dVlast /* [6] or null */) {
+  constexpr int MAXJ = NJ > 0 ? NJ : RBM_MAX_JOINTS;
+  const int nj = NJ > 0 ? NJ : nj_rt;
+  T Rs[MAXJ + 1][9];
+  T ps[MAXJ + 1][3];
+  T bs[MAXJ][6];
+  G3<T> v = g3(sp + GP_V0), w = g3(sp + GP_V0 + 3);
+  G3<T> a = g3(sp + GP_DV0), l = g3(sp + GP_DV0 + 3);
+  if (twists) {
+    twists[0] = v.x; twists[1] = v.y; twists[2] = v.z; twists[3] = w.x; twists[4] = w.y; twists[5] = w.z;
+    dtwists[0] = a.x; dtwists[1] = a.y; dtwists[2] = a.z; dtwists[3] = l.x; dtwists[4] = l.y; dtwists[5] = l.z;
+  }
+#pragma unroll
+  for (int i = 0; i < nj; ++i) {
+    const T* J = sp + GP_HEAD + GJ_STRIDE * i;
+    joint_transform(J, q[i], Rs[i], ps[i]);
+    G3<T> p = g3(ps[i]);
+    G3<T> sv = g3(J + GJ_S), sw = g3(J + GJ_S + 3);
+    G3<T> vn, wn, an, ln;
+    adjoint_apply(Rs[i], p, v, w, vn, wn);
+    adjoint_apply(Rs[i], p, a, l, an, ln);
+    v = vn + qd[i] * sv;  // Eq. 8.51
+    w = wn + qd[i] * sw;
+    // Eq. 8.52: ad(V) S = [w x s_v + v x s_w ; w x s_w]
+    a = an + qd[i] * (gcross(w, sv) + gcross(v, sw)) + qdd[i] * sv;
+    l = ln + qd[i] * gcross(w, sw) + qdd[i] * sw;
+    const T V6[6] = {v.x, v.y, v.z, w.x, w.y, w.z};
+    const T dV6[6] = {a.x, a.y, a.z, l.x, l.y, l.z};
+    if (poses) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) poses[12 * i + k] = Rs[i][k];
+      poses[12 * i + 9] = ps[i][0]; poses[12 * i + 10] = ps[i][1]; poses[12 * i + 11] = ps[i][2];
+    }
+    if (twists) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { twists[6 * (i + 1) + k] = V6[k]; dtwists[6 * (i + 1) + k] = dV6[k]; }
+    }
+    if (tau) {
+      const T* G = J + GJ_G;
+      T h[6], gd[6];  // momentum G V and inertial force G dV
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        T sh = T(0), sg = T(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { sh += G[6 * r + k] * V6[k]; sg += G[6 * r + k] * dV6[k]; }
+        h[r] = sh; gd[r] = sg;
+      }
+      // -ad(V)^T [hf; hm] = [w x hf ; v x hf + w x hm]
+      G3<T> hf = g3(h), hm = g3(h + 3);
+      G3<T> bf = g3(gd) + gcross(w, hf);
+      G3<T> bm = g3(gd + 3) + gcross(v, hf) + gcross(w, hm);
+      bs[i][0] = bf.x; bs[i][1] = bf.y; bs[i][2] = bf.z; bs[i][3] = bm.x; bs[i][4] = bm.y; bs[i][5] = bm.z;
+    }
+  }
+  if (Vlast) {
+    Vlast[0] = v.x; Vlast[1] = v.y; Vlast[2] = v.z; Vlast[3] = w.x; Vlast[4] = w.y; Vlast[5] = w.z;
+    dVlast[0] = a.x; dVlast[1] = a.y; dVlast[2] = a.z; dVlast[3] = l.x; dVlast[4] = l.y; dVlast[5] = l.z;
+  }
+  if (!tau) return;
+  // tip transform and wrench (dynamics.py:136-137)
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Rs[nj][k] = sp[GP_TIPR + k];
+  ps[nj][0] = sp[GP_TIPT]; ps[nj][1] = sp[GP_TIPT + 1]; ps[nj][2] = sp[GP_TIPT + 2];
+  G3<T> f = g3(sp + GP_FTIP), m = g3(sp + GP_FTIP + 3);
+#pragma unroll
+  for (int i = nj - 1; i >= 0; --i) {
+    const T* J = sp + GP_HEAD + GJ_STRIDE * i;
+    G3<T> fo, mo;
+    adjointT_apply(Rs[i + 1], g3(ps[i + 1]), f, m, fo, mo);   // Eq. 8.53
+    f = fo + g3(bs[i]);
+    m = mo + g3(bs[i] + 3);
+    tau[i] = f.x * J[GJ_S] + f.y * J[GJ_S + 1] + f.z * J[GJ_S + 2] + m.x * J[GJ_S + 3] + m.y * J[GJ_S + 4] + m.z * J[GJ_S + 5];  // Eq. 8.54
+  }
+}
+
+// =================================================================================================
+// Sensor-frame twists (core/simulate.py:202-209) and regressor rows (dynamics/dynamics.py:215-249)
+// =================================================================================================
+// V_s = Ad(T_sen) V ; dV_s = Ad(T_sen) dV.  The reference also adds ad(V_s) Ad(T_sen) V = ad(V_s) V_s,
+// which is identically zero (its floating-point residue there is ~1e-17); it is not evaluated here.
+template <class T>
+RBM_HD void sensor_twists(const T* R, const T* t, const T* V, const T* dV, T* Vs, T* dVs) {
+  G3<T> p = g3(t), vo, wo;
+  adjoint_apply(R, p, g3(V), g3(V + 3), vo, wo);
+  Vs[0] = vo.x; Vs[1] = vo.y; Vs[2] = vo.z; Vs[3] = wo.x; Vs[4] = wo.y; Vs[5] = wo.z;
+  adjoint_apply(R, p, g3(dV), g3(dV + 3), vo, wo);
+  dVs[0] = vo.x; dVs[1] = vo.y; dVs[2] = vo.z; dVs[3] = wo.x; dVs[4] = wo.y; dVs[5] = wo.z;
+}
+
+// Non-zero blocks of the 6x10 regressor:  top (rows 0-2, cols 0-3) = [x | [dw]x + [w]x[w]x],
+// bot (rows 3-5, cols 1-9) = [-[x]x | bullet(dw) + [w]x bullet(w)]   with x = dv + w x v.
+template <class T>
+RBM_HD void regressor_blocks(const T* V, const T* dV, T (&top)[3][4], T (&bot)[3][9]) {
+  const T vx = V[0], vy = V[1], vz = V[2], wx = V[3], wy = V[4], wz = V[5];
+  const T ax = dV[0], ay = dV[1], az = dV[2], lx = dV[3], ly = dV[4], lz = dV[5];
+  const T x0 = ax + (wy * vz - wz * vy), x1 = ay + (wz * vx - wx * vz), x2 = az + (wx * vy - wy * vx);
+  const T xx = wx * wx, yy = wy * wy, zz = wz * wz, xy = wx * wy, yz = wy * wz, zx = wz * wx;
+  top[0][0] = x0; top[0][1] = -(yy + zz); top[0][2] = xy - lz;     top[0][3] = zx + ly;
+  top[1][0] = x1; top[1][1] = xy + lz;    top[1][2] = -(xx + zz);  top[1][3] = yz - lx;
+  top[2][0] = x2; top[2][1] = zx - ly;    top[2][2] = yz + lx;     top[2][3] = -(xx + yy);
+  // -[x]x
+  bot[0][0] = T(0); bot[0][1] = x2;   bot[0][2] = -x1;
+  bot[1][0] = -x2;  bot[1][1] = T(0); bot[1][2] = x0;
+  bot[2][0] = x1;   bot[2][1] = -x0;  bot[2][2] = T(0);
+  // bullet(dw) + [w]x bullet(w), columns ixx iyy izz ixy iyz izx
+  bot[0][3] = lx;   bot[0][4] = -yz;  bot[0][5] = yz;   bot[0][6] = ly - zx; bot[0][7] = yy - zz; bot[0][8] = lz + xy;
+  bot[1][3] = zx;   bot[1][4] = ly;   bot[1][5] = -zx;  bot[1][6] = lx + yz; bot[1][7] = lz - xy; bot[1][8] = zz - xx;
+  bot[2][3] = -xy;  bot[2][4] = xy;   bot[2][5] = lz;   bot[2][6] = xx - yy; bot[2][7] = ly + zx; bot[2][8] = lx - yz;
+}
+
+}  // namespace rbm

@@ -1,0 +1,159 @@
+"""-m gpu parity tests of the batched inverse dynamics (C ABI rbm_rnea_*) against
+ (a) golden vectors produced by executing the reference's own dynamics.py (tests/golden, oracle/gen_golden.py)
+ (b) the vectorised CPU oracle (oracle/rnea_vec.py) at BASELINE.json config 2 size (2^20 samples).
+Tolerances (BASELINE.json north_star): 1e-9 relative in fp64, 1e-4 relative in fp32, norm-wise per sample."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import load_golden, model_from_golden, rel_err, sample_states, soa
+from oracle import rnea_vec as rv
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-9
+TOL32 = 1e-4
+TARGETS = ["hammer", "uniform_gearbox", "kill_la_kill"]
+GENERIC = ["nj6", "nj4", "nj9"]
+ALL = [f"ref_inverse_{t}.npz" for t in TARGETS] + [f"ref_inverse_generic_{g}.npz" for g in GENERIC]
+
+
+@pytest.mark.parametrize("fname", ALL)
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_fp64_soa_matches_reference_golden(fname, force_generic):
+    g = load_golden(fname)
+    m = model_from_golden(g, force_generic=force_generic)
+    is_target = "generic" not in fname
+    assert m.kernel_path == ("seq_iso" if (is_target and not force_generic) else "generic")
+    q, qd, qdd = soa(g["traj"])
+    tau, V, dV = m.rnea(q, qd, qdd, want_twists=True)
+    torch.cuda.synchronize()
+    nj = m.nj
+    assert rel_err(tau.t().cpu().numpy(), g["tau"]).max() < TOL64
+    assert rel_err(V.t().cpu().numpy(), g["twists"][:, nj]).max() < TOL64
+    assert rel_err(dV.t().cpu().numpy(), g["dtwists"][:, nj]).max() < TOL64
+    tau2 = m.rnea(q, qd, qdd)
+    assert torch.equal(tau, tau2)  # with / without the twist outputs: same arithmetic
+
+
+@pytest.mark.parametrize("fname", ALL)
+def test_fp64_aos_and_full_state(fname):
+    g = load_golden(fname)
+    m = model_from_golden(g)
+    traj = torch.as_tensor(g["traj"], device="cuda")
+    tau = m.rnea_aos(traj)
+    assert rel_err(tau.cpu().numpy(), g["tau"]).max() < TOL64
+    tau_f, poses, tw, dtw = m.rnea_full(traj)
+    assert rel_err(tau_f.cpu().numpy(), g["tau"]).max() < TOL64
+    assert np.abs(poses.cpu().numpy() - g["poses"]).max() < 1e-12
+    assert rel_err(tw.cpu().numpy(), g["twists"]).max() < TOL64
+    assert rel_err(dtw.cpu().numpy(), g["dtwists"]).max() < TOL64
+
+
+@pytest.mark.parametrize("fname", ALL)
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_fp32_mode(fname, force_generic):
+    g = load_golden(fname)
+    m = model_from_golden(g, force_generic=force_generic)
+    q, qd, qdd = soa(g["traj"], torch.float32)
+    tau = m.rnea(q, qd, qdd)
+    assert tau.dtype == torch.float32
+    assert rel_err(tau.t().cpu().numpy(), g["tau"]).max() < TOL32
+    tau_aos = m.rnea_aos(torch.as_tensor(g["traj"], dtype=torch.float32, device="cuda"))
+    assert rel_err(tau_aos.cpu().numpy(), g["tau"]).max() < TOL32
+
+
+def test_static_gravity_known_answer():
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    traj = np.zeros((1, 3, 6))
+    traj[0, 0] = g["key_qpos"]
+    tau = m.rnea_aos(torch.as_tensor(traj, device="cuda")).cpu().numpy()[0]
+    assert abs(tau[2] - (32.0 + float(g["gt_mass"])) * 9.81) < 1e-9
+    assert np.abs(tau[[0, 1]]).max() < 1e-9
+
+
+def test_config1_planned_trajectory():
+    """BASELINE.json config 1 (open-loop part): tau for all 1500 planned steps of base.yaml, V6/dV6 included."""
+    g = load_golden("ref_inverse_hammer.npz")
+    c1 = load_golden("ref_config1_hammer.npz")
+    m = model_from_golden(g)
+    q, qd, qdd = soa(c1["traj"])
+    tau, V, dV = m.rnea(q, qd, qdd, want_twists=True)
+    assert rel_err(tau.t().cpu().numpy(), c1["tau"]).max() < TOL64
+    assert rel_err(V.t().cpu().numpy(), c1["twist6"], 1e-3).max() < TOL64
+    assert rel_err(dV.t().cpu().numpy(), c1["dtwist6"], 1e-3).max() < TOL64
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 127, 128, 129, 1000])
+def test_ragged_sizes(n):
+    g = load_golden("ref_inverse_uniform_gearbox.npz")
+    m = model_from_golden(g)
+    rng = np.random.default_rng(n)
+    traj = sample_states(rng, n)
+    ref = rv.inverse_batched(traj, g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"])["tau"] if n else np.zeros((0, 6))
+    q, qd, qdd = soa(traj) if n else tuple(torch.empty((6, 0), dtype=torch.float64, device="cuda") for _ in range(3))
+    tau = m.rnea(q, qd, qdd).t().cpu().numpy()
+    tau_aos = m.rnea_aos(torch.as_tensor(traj, device="cuda").reshape(n, 3, 6)).cpu().numpy()
+    if n:
+        assert rel_err(tau, ref).max() < TOL64
+        assert rel_err(tau_aos, ref).max() < TOL64
+    else:
+        assert tau.shape == (0, 6) and tau_aos.shape == (0, 6)
+
+
+def test_config2_one_million_samples_fp64():
+    """BASELINE.json config 2: 2^20 synthetic samples, fp64, every sample checked against the vectorised oracle."""
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    n = 1 << 20
+    traj = sample_states(np.random.default_rng(0), n)
+    q, qd, qdd = soa(traj)
+    tau = m.rnea(q, qd, qdd).t().cpu().numpy()
+    worst = 0.0
+    for s0 in range(0, n, 1 << 16):
+        sl = slice(s0, s0 + (1 << 16))
+        ref = rv.inverse_batched(traj[sl], g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"])["tau"]
+        worst = max(worst, rel_err(tau[sl], ref).max())
+    assert worst < TOL64, worst
+    # size-independent property at full size: tau is affine in qdd  (tau(q,qd,2a) - tau(q,qd,a) == tau(q,qd,a) - tau(q,qd,0))
+    t0 = m.rnea(q, qd, torch.zeros_like(qdd))
+    t1 = m.rnea(q, qd, qdd)
+    t2 = m.rnea(q, qd, 2 * qdd)
+    lin = ((t2 - t1) - (t1 - t0)).abs().max().item()
+    assert lin < 1e-9 * t1.abs().max().item()
+
+
+def test_host_end_to_end_path():
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    n = 300_000
+    traj = sample_states(np.random.default_rng(5), n)
+    tau_dev = m.rnea_aos(torch.as_tensor(traj, device="cuda")).cpu().numpy()
+    tau_host = m.rnea_host(traj, chunk=65536)
+    assert np.array_equal(tau_host, tau_dev)
+    pinned = torch.as_tensor(traj).pin_memory()
+    tau_p = m.rnea_host(pinned)
+    assert np.array_equal(tau_p.numpy(), tau_dev)
+    t32 = m.rnea_host(traj.astype(np.float32))
+    assert rel_err(t32, tau_dev).max() < TOL32
+
+
+def test_invalid_arguments_raise():
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    q = torch.zeros((6, 4), dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):
+        m.rnea(q, q, torch.zeros((6, 5), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        m.rnea(q.cpu(), q.cpu(), q.cpu())  # no CPU path
+    with pytest.raises(ValueError):
+        m.rnea(q.half(), q.half(), q.half())
+    from rigid_body_manipulation_b200.engine import Model
+
+    with pytest.raises(ValueError):
+        Model(g["hposes_Rt"][:-1], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"])
+    bad = g["simats"].copy()
+    bad[3, 2, 2] = np.nan
+    with pytest.raises(ValueError):
+        Model(g["hposes_Rt"], bad, g["uscrews"], g["twist_0"], g["dtwist_0"])
