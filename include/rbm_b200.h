@@ -107,6 +107,69 @@ RBM_API int rbm_rnea_full_f64(const rbm_model* m, const double* traj, double* ta
 RBM_API int rbm_rnea_host_f64(const rbm_model* m, const double* traj_host, double* tau_host, int64_t n, int64_t chunk);
 RBM_API int rbm_rnea_host_f32(const rbm_model* m, const float* traj_host, float* tau_host, int64_t n, int64_t chunk);
 
+/* ---- sensor-frame regressor and identification ------------------------------------------------------
+ * Parameter order phi = [m, m cx, m cy, m cz, Ixx, Iyy, Izz, Ixy, Iyz, Izx] (dynamics.py:225-230, loggers.py:133),
+ * inertia about the sensor-frame origin; regressor rows are [force (3); torque (3)]. */
+
+/* get_regressor_matrix (dynamics/dynamics.py:215-249), batched, AoS: twists, dtwists [n][6] -> Y [n][6][10]. */
+RBM_API int rbm_regressor_rows_f64(const double* twists, const double* dtwists, double* Y, int64_t n, void* stream);
+
+/* Twists of the last link into the sensor frame (core/simulate.py:202-209), AoS [n][6]:
+ * V_s = Ad(T) V, dV_s = Ad(T) dV with T = pose_Rt (HOST pointer, 12 scalars). */
+RBM_API int rbm_sensor_twists_f64(const double* pose_Rt, const double* twists, const double* dtwists, double* twists_sen, double* dtwists_sen,
+                          int64_t n, void* stream);
+
+/* Fused (q, qd, qdd) [nj][ld] -> forward sweep -> sensor frame (the model's pose_sen_Rt) -> any of:
+ *   Y          [n][6][10]  materialised regressor rows               (NULL to skip)
+ *   twist_sen, dtwist_sen [6][ld]                                     (NULL to skip, only together)
+ *   wrench     [6][ld] = Y phi with phi a DEVICE pointer to 10 scalars (both NULL to skip): the load a body with
+ *              parameters phi puts on the sensor -- used to synthesise F/T data for identification benchmarks. */
+RBM_API int rbm_regressor_from_traj_f64(const rbm_model* m, const double* q, const double* qd, const double* qdd, double* Y, double* twist_sen,
+                                double* dtwist_sen, const double* phi, double* wrench, int64_t n, int64_t ld, void* stream);
+RBM_API int rbm_regressor_from_traj_f32(const rbm_model* m, const float* q, const float* qd, const float* qdd, float* Y, float* twist_sen,
+                                float* dtwist_sen, const float* phi, float* wrench, int64_t n, int64_t ld, void* stream);
+
+/* Normal equations of the stacked least-squares problem of loggers/loggers.py:127-129 without materialising Y:
+ *   gram_pack [112] (device, always double) = [Y^T Y (100, row-major) | Y^T f (10) | f^T f | n]
+ *   f [6][ld]: measured wrench per sample in the sensor frame.
+ *   workspace: device scratch of rbm_gram_workspace_bytes() bytes (per-block partial sums; no atomics, the
+ *   reduction order is fixed, so results are bit-reproducible for a given n).
+ * The fp32 entry point reads float inputs, forms the regressor in float and accumulates in double every 16 samples. */
+RBM_API size_t rbm_gram_workspace_bytes(const rbm_model* m, int64_t n);
+RBM_API int rbm_regressor_gram_f64(const rbm_model* m, const double* q, const double* qd, const double* qdd, const double* f, double* gram_pack,
+                           void* workspace, size_t workspace_bytes, int64_t n, int64_t ld, void* stream);
+RBM_API int rbm_regressor_gram_f32(const rbm_model* m, const float* q, const float* qd, const float* qdd, const float* f, double* gram_pack,
+                           void* workspace, size_t workspace_bytes, int64_t n, int64_t ld, void* stream);
+
+/* ---- LQR linearisation ------------------------------------------------------------------------------------
+ * Replaces dynamics.StateSpace.update_matrices (dynamics/dynamics.py:41-46 -> mjd_transitionFD, consumed by
+ * controllers/lqr.py:43-49) for the reference's plant (nv = nu = nj, unit-gear motors, semi-implicit Euler with
+ * step dt): x = [q; qd], x+ = f(x, u);  A = df/dx (2nj x 2nj), B = df/du (2nj x nj), by finite differences of the
+ * batched inverse dynamics (step eps, centred or forward -- StateSpaceConfig.epsilon / .centered, dynamics.py:14-17).
+ *   q, qd : [nj][ld];  u : [nj][ld] applied joint forces (ctrl), or NULL = zeros
+ *   A : [(2nj*2nj)][ld] element-major: entry (r, c) of state s at A[(r*2nj + c)*ld + s];  B : [(2nj*nj)][ld] likewise
+ *   qdd : [nj][ld] or NULL -- the nominal forward-dynamics acceleration M^-1 (u - h), a by-product. */
+RBM_API int rbm_linearize_f64(const rbm_model* m, const double* q, const double* qd, const double* u, double dt, double eps, int centered,
+                      double* A, double* B, double* qdd, int64_t n, int64_t ld, void* stream);
+
+/* ---- frame algebra helpers, batched (device pointers, AoS) ----------------------------------------------
+ * transfer_simat (dynamics/dynamics.py:72-106): out[s] = Ad(T_s^-1)^T G_s Ad(T_s^-1); poses [n][12], simats [n][36]. */
+RBM_API int rbm_transfer_simat_f64(const double* poses_Rt, const double* simats, double* out, int64_t n, void* stream);
+/* coordinate_transfer_simat (dynamics.py:260-263): out[s] = Ad(T_s) G_s Ad(T_s)^T. */
+RBM_API int rbm_coordinate_transfer_simat_f64(const double* poses_Rt, const double* simats, double* out, int64_t n, void* stream);
+/* coordinate_transfer_imat (dynamics.py:252-257): out[s] = R I R^T + m (|t|^2 1 - t t^T); imats [n][9], mass [n]. */
+RBM_API int rbm_coordinate_transfer_imat_f64(const double* poses_Rt, const double* imats, const double* mass, double* out, int64_t n, void* stream);
+/* get_spatial_inertia_matrix (dynamics.py:49-69): mass [n], diag [n][3] -> [n][36]. */
+RBM_API int rbm_spatial_inertia_f64(const double* mass, const double* diag, double* out, int64_t n, void* stream);
+/* compose / tq2se3 / tr2se3 (transformations/transformations.py:8-50): trans [n][3] + rot [n][rot_len] (rot_len 4: wxyz
+ * quaternion, 9: row-major rotation matrix) -> poses [n][12]; status [n] (device int32): 0 ok, 1 non-unit quaternion,
+ * 2 invalid rotation matrix (the conditions under which liegroups raises ValueError). */
+RBM_API int rbm_compose_f64(const double* trans, const double* rot, int rot_len, double* poses_Rt, int32_t* status, int64_t n, void* stream);
+/* extract_linvel / extract_linacc_frame_transferred (dynamics.py:160-212): twists, dtwists [n][6], points [n][3] ->
+ * linvel, linacc [n][3] (either output may be NULL; dtwists may be NULL when linacc is). */
+RBM_API int rbm_point_motion_f64(const double* twists, const double* dtwists, const double* points, double* linvel, double* linacc, int64_t n,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -253,6 +253,23 @@ def golden_config1(ns, c, planner_out, name):
     )
 
 
+def golden_mjmodel(name):
+    """The MjModel / MjData look-alike arrays (oracle/mjcf_subset.py) for one target, so that the GPU box -- which has
+    neither MuJoCo nor the reference's XML -- can exercise the product's MuJoCo bridge (constants_from_mujoco, Poses)."""
+    from . import mjcf_subset as mj
+
+    gt = mj.target_ground_truth(mj.read_cad_row(os.path.join(XML, "targets", name, "object_cad_gt.csv")))
+    m = mj.compile_manipulator_with_target(os.path.join(XML, "manipulators", "sequential.xml"), gt)
+    d = mj.kinematics(m, m.key_qpos)
+    np.savez_compressed(
+        os.path.join(GOLD, f"ref_mjmodel_{name}.npz"),
+        body_names=np.array(m.body_names), site_names=np.array(m.site_names), body_pos=m.body_pos, body_quat=m.body_quat,
+        body_ipos=m.body_ipos, body_iquat=m.body_iquat, body_mass=m.body_mass, body_inertia=m.body_inertia, jnt_type=m.jnt_type,
+        jnt_axis=m.jnt_axis, jnt_pos=m.jnt_pos, gravity=m.gravity, key_qpos=m.key_qpos, qpos=d.qpos, xpos=d.xpos, xmat=d.xmat,
+        xipos=d.xipos, ximat=d.ximat, site_xpos=d.site_xpos, site_xmat=d.site_xmat,
+    )
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ns = rl.load()
@@ -265,6 +282,7 @@ def main():
     golden_setup_functions(ns, seed=99)
     pl = golden_planner(ns)
     golden_config1(ns, c_h, pl, "hammer")
+    golden_mjmodel("hammer")
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

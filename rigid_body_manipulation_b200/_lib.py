@@ -51,6 +51,20 @@ SIGNATURES = {
     "rbm_rnea_full_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "rbm_rnea_host_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64]),
     "rbm_rnea_host_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i64]),
+    "rbm_regressor_rows_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "rbm_sensor_twists_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "rbm_regressor_from_traj_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "rbm_regressor_from_traj_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "rbm_gram_workspace_bytes": (C.c_size_t, [_vp, _i64]),
+    "rbm_regressor_gram_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i64, _i64, _vp]),
+    "rbm_regressor_gram_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i64, _i64, _vp]),
+    "rbm_linearize_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "rbm_transfer_simat_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "rbm_coordinate_transfer_simat_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "rbm_coordinate_transfer_imat_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "rbm_spatial_inertia_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "rbm_compose_f64": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _i64, _vp]),
+    "rbm_point_motion_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
 }
 
 

@@ -319,4 +319,114 @@ int rbm_rnea_host_f32(const rbm_model* m, const float* traj_host, float* tau_hos
   return rnea_host<float>(m, traj_host, tau_host, n, chunk);
 }
 
+
+// ---- regressor / identification ------------------------------------------------------------------
+int rbm_regressor_rows_f64(const double* twists, const double* dtwists, double* Y, int64_t n, void* stream) {
+  if (n < 0) return invalid("rbm_regressor_rows_f64: n < 0");
+  if (n == 0) return RBM_OK;
+  if (!twists || !dtwists || !Y) return invalid("rbm_regressor_rows_f64: NULL pointer");
+  return launch_regressor_rows<double>(twists, dtwists, Y, n, (cudaStream_t)stream);
+}
+
+int rbm_sensor_twists_f64(const double* pose_Rt, const double* twists, const double* dtwists, double* twists_sen, double* dtwists_sen, int64_t n,
+                          void* stream) {
+  if (n < 0) return invalid("rbm_sensor_twists_f64: n < 0");
+  if (n == 0) return RBM_OK;
+  if (!pose_Rt || !twists || !dtwists || !twists_sen || !dtwists_sen) return invalid("rbm_sensor_twists_f64: NULL pointer");
+  return launch_sensor_twists<double>(pose_Rt, twists, dtwists, twists_sen, dtwists_sen, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+namespace {
+template <class T>
+int regressor_from_traj(const char* name, const rbm_model* m, const T* q, const T* qd, const T* qdd, T* Y, T* Vs, T* dVs, const T* phi, T* F, int64_t n,
+                        int64_t ld, void* stream) {
+  if (!m) return invalid(std::string(name) + ": model is NULL");
+  if (n < 0) return invalid(std::string(name) + ": n < 0");
+  if (n == 0) return RBM_OK;
+  if (!q || !qd || !qdd) return invalid(std::string(name) + ": NULL batch pointer");
+  if (ld < n) return invalid(std::string(name) + ": ld < n");
+  if ((Vs == nullptr) != (dVs == nullptr)) return invalid(std::string(name) + ": twist_sen and dtwist_sen go together");
+  if ((phi == nullptr) != (F == nullptr)) return invalid(std::string(name) + ": phi and wrench go together");
+  return launch_regressor_from_traj<T>(m, q, qd, qdd, Y, Vs, dVs, phi, F, n, ld, (cudaStream_t)stream);
+}
+template <class T>
+int regressor_gram(const char* name, const rbm_model* m, const T* q, const T* qd, const T* qdd, const T* f, double* pack, void* ws, size_t ws_bytes,
+                   int64_t n, int64_t ld, void* stream) {
+  if (!m) return invalid(std::string(name) + ": model is NULL");
+  if (n < 0) return invalid(std::string(name) + ": n < 0");
+  if (!pack || !ws) return invalid(std::string(name) + ": NULL gram_pack / workspace");
+  if (n > 0 && (!q || !qd || !qdd || !f)) return invalid(std::string(name) + ": NULL batch pointer");
+  if (ld < n) return invalid(std::string(name) + ": ld < n");
+  if (ws_bytes < rbm_gram_workspace_bytes(m, n)) return invalid(std::string(name) + ": workspace too small (see rbm_gram_workspace_bytes)");
+  return launch_regressor_gram<T>(m, q, qd, qdd, f, pack, static_cast<double*>(ws), n, ld, (cudaStream_t)stream);
+}
+}  // namespace
+
+extern "C" {
+
+int rbm_regressor_from_traj_f64(const rbm_model* m, const double* q, const double* qd, const double* qdd, double* Y, double* twist_sen,
+                                double* dtwist_sen, const double* phi, double* wrench, int64_t n, int64_t ld, void* stream) {
+  return regressor_from_traj<double>("rbm_regressor_from_traj_f64", m, q, qd, qdd, Y, twist_sen, dtwist_sen, phi, wrench, n, ld, stream);
+}
+int rbm_regressor_from_traj_f32(const rbm_model* m, const float* q, const float* qd, const float* qdd, float* Y, float* twist_sen, float* dtwist_sen,
+                                const float* phi, float* wrench, int64_t n, int64_t ld, void* stream) {
+  return regressor_from_traj<float>("rbm_regressor_from_traj_f32", m, q, qd, qdd, Y, twist_sen, dtwist_sen, phi, wrench, n, ld, stream);
+}
+
+size_t rbm_gram_workspace_bytes(const rbm_model* m, int64_t n) {
+  if (!m) return 0;
+  return sizeof(double) * 70 * (size_t)gram_grid(m, n < 0 ? 0 : n);
+}
+int rbm_regressor_gram_f64(const rbm_model* m, const double* q, const double* qd, const double* qdd, const double* f, double* gram_pack,
+                           void* workspace, size_t workspace_bytes, int64_t n, int64_t ld, void* stream) {
+  return regressor_gram<double>("rbm_regressor_gram_f64", m, q, qd, qdd, f, gram_pack, workspace, workspace_bytes, n, ld, stream);
+}
+int rbm_regressor_gram_f32(const rbm_model* m, const float* q, const float* qd, const float* qdd, const float* f, double* gram_pack, void* workspace,
+                           size_t workspace_bytes, int64_t n, int64_t ld, void* stream) {
+  return regressor_gram<float>("rbm_regressor_gram_f32", m, q, qd, qdd, f, gram_pack, workspace, workspace_bytes, n, ld, stream);
+}
+
+int rbm_linearize_f64(const rbm_model* m, const double* q, const double* qd, const double* u, double dt, double eps, int centered, double* A,
+                      double* B, double* qdd, int64_t n, int64_t ld, void* stream) {
+  RBM_CHECK_BATCH("rbm_linearize_f64")
+  if (!q || !qd || !A || !B) return invalid("rbm_linearize_f64: NULL batch pointer");
+  if (ld < n) return invalid("rbm_linearize_f64: ld < n");
+  if (!(dt > 0.0) || !(eps > 0.0)) return invalid("rbm_linearize_f64: dt and eps must be positive");
+  return launch_linearize<double>(m, q, qd, u, dt, eps, centered, A, B, qdd, n, ld, (cudaStream_t)stream);
+}
+
+// ---- frame algebra helpers ------------------------------------------------------------------------
+#define RBM_SIMPLE_CHECK(name, cond)                       \
+  if (n < 0) return invalid(name ": n < 0");               \
+  if (n == 0) return RBM_OK;                               \
+  if (!(cond)) return invalid(name ": NULL pointer");
+
+int rbm_transfer_simat_f64(const double* poses_Rt, const double* simats, double* out, int64_t n, void* stream) {
+  RBM_SIMPLE_CHECK("rbm_transfer_simat_f64", poses_Rt && simats && out)
+  return launch_transfer_simat(poses_Rt, simats, out, n, 12, 36, 0, (cudaStream_t)stream);
+}
+int rbm_coordinate_transfer_simat_f64(const double* poses_Rt, const double* simats, double* out, int64_t n, void* stream) {
+  RBM_SIMPLE_CHECK("rbm_coordinate_transfer_simat_f64", poses_Rt && simats && out)
+  return launch_transfer_simat(poses_Rt, simats, out, n, 12, 36, 1, (cudaStream_t)stream);
+}
+int rbm_coordinate_transfer_imat_f64(const double* poses_Rt, const double* imats, const double* mass, double* out, int64_t n, void* stream) {
+  RBM_SIMPLE_CHECK("rbm_coordinate_transfer_imat_f64", poses_Rt && imats && mass && out)
+  return launch_transfer_imat(poses_Rt, imats, mass, out, n, (cudaStream_t)stream);
+}
+int rbm_spatial_inertia_f64(const double* mass, const double* diag, double* out, int64_t n, void* stream) {
+  RBM_SIMPLE_CHECK("rbm_spatial_inertia_f64", mass && diag && out)
+  return launch_spatial_inertia(mass, diag, out, n, (cudaStream_t)stream);
+}
+int rbm_compose_f64(const double* trans, const double* rot, int rot_len, double* poses_Rt, int32_t* status, int64_t n, void* stream) {
+  if (rot_len != 4 && rot_len != 9) return invalid("rbm_compose_f64: rot_len must be 4 (wxyz quaternion) or 9 (rotation matrix)");
+  RBM_SIMPLE_CHECK("rbm_compose_f64", trans && rot && poses_Rt && status)
+  return launch_compose(trans, rot, rot_len, poses_Rt, status, n, (cudaStream_t)stream);
+}
+int rbm_point_motion_f64(const double* twists, const double* dtwists, const double* points, double* linvel, double* linacc, int64_t n, void* stream) {
+  RBM_SIMPLE_CHECK("rbm_point_motion_f64", twists && points && (linvel || linacc) && (!linacc || dtwists))
+  return launch_point_motion(twists, dtwists, points, linvel, linacc, n, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -58,4 +58,30 @@ int launch_rnea_aos(const rbm_model* m, const T* traj, T* tau, int64_t n, cudaSt
 template <class T>
 int launch_rnea_full(const rbm_model* m, const T* traj, T* tau, T* poses, T* twists, T* dtwists, int64_t n, cudaStream_t st);
 
+
+// launchers (rbm_regressor.cu)
+int gram_grid(const rbm_model* m, int64_t n);
+template <class T>
+int launch_regressor_rows(const T* tw, const T* dtw, T* Y, int64_t n, cudaStream_t st);
+template <class T>
+int launch_sensor_twists(const double* pose_Rt, const T* tw, const T* dtw, T* tws, T* dtws, int64_t n, cudaStream_t st);
+template <class T>
+int launch_regressor_from_traj(const rbm_model* m, const T* q, const T* qd, const T* qdd, T* Y, T* Vs, T* dVs, const T* phi, T* F, int64_t n, int64_t ld,
+                               cudaStream_t st);
+template <class T>
+int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* qdd, const T* f, double* pack, double* partials, int64_t n, int64_t ld,
+                          cudaStream_t st);
+
+// launcher (rbm_linearize.cu)
+template <class T>
+int launch_linearize(const rbm_model* m, const T* q, const T* qd, const T* u, double dt, double eps, int centered, T* A, T* B, T* qdd, int64_t n,
+                     int64_t ld, cudaStream_t st);
+
+// launchers (rbm_setup.cu)
+int launch_transfer_simat(const double* poses, const double* simats, double* out, int64_t n, int pose_stride, int simat_stride, int mode, cudaStream_t st);
+int launch_transfer_imat(const double* poses, const double* imats, const double* mass, double* out, int64_t n, cudaStream_t st);
+int launch_spatial_inertia(const double* mass, const double* diag, double* out, int64_t n, cudaStream_t st);
+int launch_compose(const double* trans, const double* rot, int rot_len, double* out, int* status, int64_t n, cudaStream_t st);
+int launch_point_motion(const double* tw, const double* dtw, const double* pts, double* linvel, double* linacc, int64_t n, cudaStream_t st);
+
 }  // namespace rbm

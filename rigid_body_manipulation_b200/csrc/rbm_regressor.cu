@@ -1,0 +1,355 @@
+// Sensor-frame regressor and its Gram accumulation (inertial-parameter identification).
+//
+// Replaces, batched and fused:  core/simulate.py:202-209 (twists into the F/T sensor frame),
+// dynamics/dynamics.py:215-249 (get_regressor_matrix, 6x10 per sample) and the stacking +
+// np.linalg.lstsq of loggers/loggers.py:127-129, which is re-expressed as normal equations: the kernel
+// accumulates  [Y f]^T [Y f]  (Y^T Y 10x10, Y^T f 10, f^T f) and never writes Y to HBM.
+//
+// Gram kernel: persistent grid, one sample per thread per iteration; each thread keeps the 70 distinct
+// non-zero entries of the two diagonal blocks in registers, blocks reduce with warp shuffles + shared
+// memory, and a second single-block kernel sums the per-block partials in a FIXED order (deterministic
+// result for a given grid).  HBM traffic per sample: q, qd, qdd, f = 24 scalars read, nothing written.
+#include "rbm_internal.h"
+#include "rbm_rnea.cuh"
+
+namespace rbm {
+
+constexpr int kRowsBlock = 128;
+constexpr int kGramBlock = 256;
+constexpr int kTop = 15;             // 5x5 symmetric: [x | X | f_force]
+constexpr int kBot = 55;             // 10x10 symmetric: [-[x]x | Yb | f_torque]
+constexpr int kAcc = kTop + kBot;    // 70
+
+// ---- last-link twist for one sample, any kernel path ------------------------------------------------
+template <class T, int PATH>
+__device__ __forceinline__ void last_link_twists(const FastParams<T>& P, const T* sp, int nj, const T* __restrict__ q, const T* __restrict__ qd,
+                                                 const T* __restrict__ qdd, int64_t s, int64_t ld, T* V, T* dV) {
+  if constexpr (PATH == PATH_GENERIC) {
+    T rq[RBM_MAX_JOINTS], rqd[RBM_MAX_JOINTS], rqdd[RBM_MAX_JOINTS];
+    for (int j = 0; j < nj; ++j) { rq[j] = __ldg(q + j * ld + s); rqd[j] = __ldg(qd + j * ld + s); rqdd[j] = __ldg(qdd + j * ld + s); }
+    generic_rnea<T, 0>(sp, sp, nj, rq, rqd, rqdd, (T*)nullptr, nullptr, nullptr, nullptr, V, dV);
+  } else {
+    T rq[6], rqd[6], rqdd[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { rq[j] = __ldg(q + j * ld + s); rqd[j] = __ldg(qd + j * ld + s); rqdd[j] = __ldg(qdd + j * ld + s); }
+    FastResult<T> r;
+    if constexpr (PATH == PATH_SEQ_ISO) fast_rnea<T, SeqIso, false>(P, rq, rqd, rqdd, r);
+    else fast_rnea<T, SeqRigid, false>(P, rq, rqd, rqdd, r);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { V[k] = r.v[k]; V[3 + k] = r.w[k]; dV[k] = r.a[k]; dV[3 + k] = r.l[k]; }
+  }
+}
+
+template <class T>
+__device__ __forceinline__ const T* sensor_R(const FastParams<T>& P, const T* sp, bool generic) { return generic ? sp + GP_SENR : P.senR; }
+
+// ---------------------------------------------------------------------------------------------
+// regressor rows from given twists (get_regressor_matrix, dynamics.py:215-249), AoS
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void store_rows(const T (&top)[3][4], const T (&bot)[3][9], T* __restrict__ Y) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 10; ++c) {
+      Y[r * 10 + c] = c < 4 ? top[r][c] : T(0);
+      Y[(3 + r) * 10 + c] = c == 0 ? T(0) : bot[r][c - 1];
+    }
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kRowsBlock) k_regressor_rows(const T* __restrict__ tw, const T* __restrict__ dtw, T* __restrict__ Y, int64_t n) {
+  const int64_t s = (int64_t)blockIdx.x * kRowsBlock + threadIdx.x;
+  if (s >= n) return;
+  T V[6], dV[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { V[k] = tw[s * 6 + k]; dV[k] = dtw[s * 6 + k]; }
+  T top[3][4], bot[3][9];
+  regressor_blocks(V, dV, top, bot);
+  store_rows(top, bot, Y + s * 60);
+}
+
+// sensor-frame twists from last-link twists, AoS (core/simulate.py:202-209)
+template <class T>
+struct PoseArg { T R[9]; T t[3]; };
+
+template <class T>
+__global__ void __launch_bounds__(kRowsBlock) k_sensor_twists(const __grid_constant__ PoseArg<T> pose, const T* __restrict__ tw, const T* __restrict__ dtw,
+                                                              T* __restrict__ tws, T* __restrict__ dtws, int64_t n) {
+  const int64_t s = (int64_t)blockIdx.x * kRowsBlock + threadIdx.x;
+  if (s >= n) return;
+  T V[6], dV[6], Vs[6], dVs[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { V[k] = tw[s * 6 + k]; dV[k] = dtw[s * 6 + k]; }
+  sensor_twists(pose.R, pose.t, V, dV, Vs, dVs);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { tws[s * 6 + k] = Vs[k]; dtws[s * 6 + k] = dVs[k]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused: (q, qd, qdd) -> sensor-frame twists -> regressor rows / predicted wrench
+// ---------------------------------------------------------------------------------------------
+template <class T, int PATH>
+__global__ void __launch_bounds__(kRowsBlock) k_regressor_from_traj(const __grid_constant__ FastParams<T> P, const T* __restrict__ gp, int nj, int nparams,
+                                                                    const T* __restrict__ q, const T* __restrict__ qd, const T* __restrict__ qdd,
+                                                                    T* __restrict__ Y /* [n][60] or null */, T* __restrict__ Vs_out /* [6][ld] or null */,
+                                                                    T* __restrict__ dVs_out, const T* __restrict__ phi /* [10] device or null */,
+                                                                    T* __restrict__ F_out /* [6][ld] or null */, int64_t n, int64_t ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sp = reinterpret_cast<T*>(smem_raw);
+  if constexpr (PATH == PATH_GENERIC) {
+    for (int i = threadIdx.x; i < nparams; i += blockDim.x) sp[i] = gp[i];
+    __syncthreads();
+  }
+  const int64_t s = (int64_t)blockIdx.x * kRowsBlock + threadIdx.x;
+  if (s >= n) return;
+  T V[6], dV[6], Vs[6], dVs[6];
+  last_link_twists<T, PATH>(P, sp, nj, q, qd, qdd, s, ld, V, dV);
+  const T* R = sensor_R(P, sp, PATH == PATH_GENERIC);
+  sensor_twists(R, R + 9, V, dV, Vs, dVs);
+  if (Vs_out) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { Vs_out[k * ld + s] = Vs[k]; dVs_out[k * ld + s] = dVs[k]; }
+  }
+  if (!Y && !F_out) return;
+  T top[3][4], bot[3][9];
+  regressor_blocks(Vs, dVs, top, bot);
+  if (Y) store_rows(top, bot, Y + s * 60);
+  if (F_out) {  // F = Y phi : the wrench a body with parameters phi would load the sensor with
+    T ph[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) ph[k] = __ldg(phi + k);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      T f = T(0), m = T(0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) f += top[r][c] * ph[c];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) m += bot[r][c] * ph[1 + c];
+      F_out[r * ld + s] = f;
+      F_out[(3 + r) * ld + s] = m;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram accumulation
+// ---------------------------------------------------------------------------------------------
+// structural zeros of the bottom block: -[x]x has a zero diagonal (rows 0..2 x cols 0..2)
+__host__ __device__ constexpr bool bot_nz(int r, int c) { return !(c < 3 && c == r); }
+
+// acc layout: [0,15) upper triangle of U^T U (5x5, row-major i<=j), [15,70) upper triangle of W^T W (10x10)
+template <class TA, class T>
+__device__ __forceinline__ void gram_accumulate(TA (&acc)[kAcc], const T (&top)[3][4], const T (&bot)[3][9], const T (&f)[6]) {
+  // U = [top | f_force] (3x5), W = [bot | f_torque] (3x10)
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    TA u[5], w[10];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) u[c] = (TA)top[r][c];
+    u[4] = (TA)f[r];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) w[c] = (TA)bot[r][c];
+    w[9] = (TA)f[3 + r];
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = i; j < 5; ++j) { acc[k] += u[i] * u[j]; ++k; }
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+#pragma unroll
+      for (int j = i; j < 10; ++j) {
+        if (bot_nz(r, i) && bot_nz(r, j)) acc[k] += w[i] * w[j];
+        ++k;
+      }
+  }
+}
+
+template <class T, int PATH>
+__global__ void __launch_bounds__(kGramBlock, 1) k_regressor_gram(const __grid_constant__ FastParams<T> P, const T* __restrict__ gp, int nj, int nparams,
+                                                                  const T* __restrict__ q, const T* __restrict__ qd, const T* __restrict__ qdd,
+                                                                  const T* __restrict__ f, double* __restrict__ partials /* [grid][kAcc] */,
+                                                                  int64_t n, int64_t ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sp = reinterpret_cast<T*>(smem_raw);
+  if constexpr (PATH == PATH_GENERIC) {
+    for (int i = threadIdx.x; i < nparams; i += blockDim.x) sp[i] = gp[i];
+  }
+  __shared__ double red[kGramBlock / 32][kAcc];
+  __syncthreads();
+  // fp64: products accumulate directly in double registers.  fp32: products accumulate in float registers for
+  // kFlush samples, then the warp's partial sums are reduced and added to double accumulators in shared memory.
+  using TA = T;
+  constexpr int kFlush = 16;
+  TA acc[kAcc];
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[k] = TA(0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = lane; k < kAcc; k += 32) red[warp][k] = 0.0;
+  __syncwarp();
+  const T* R = sensor_R(P, sp, PATH == PATH_GENERIC);
+  const int64_t stride = (int64_t)gridDim.x * kGramBlock;
+  // every lane of a warp runs the same number of iterations so the periodic warp reduction stays convergent
+  const int64_t first = (int64_t)blockIdx.x * kGramBlock + warp * 32;
+  int since_flush = 0;
+  for (int64_t base = first; base < n; base += stride) {
+    const int64_t s = base + lane;
+    if (s < n) {
+      T V[6], dV[6], Vs[6], dVs[6], fs[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) fs[k] = __ldg(f + k * ld + s);
+      last_link_twists<T, PATH>(P, sp, nj, q, qd, qdd, s, ld, V, dV);
+      sensor_twists(R, R + 9, V, dV, Vs, dVs);
+      T top[3][4], bot[3][9];
+      regressor_blocks(Vs, dVs, top, bot);
+      gram_accumulate(acc, top, bot, fs);
+    }
+    if constexpr (sizeof(T) == 4) {
+      if (++since_flush == kFlush) {
+        since_flush = 0;
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) {
+          float v = acc[k];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == (k & 31)) red[warp][k] += (double)v;
+          acc[k] = 0.f;
+        }
+      }
+    }
+  }
+  // final warp reduction into red[warp][*]
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) {
+    if constexpr (sizeof(T) == 4) {
+      float v = acc[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == (k & 31)) red[warp][k] += (double)v;
+    } else {
+      double v = acc[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == (k & 31)) red[warp][k] += v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    double v = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < kGramBlock / 32; ++wq) v += red[wq][threadIdx.x];  // fixed order
+    partials[(int64_t)blockIdx.x * kAcc + threadIdx.x] = v;
+  }
+}
+
+// partials [nblocks][70] -> pack [112] = [Y^T Y (100, row-major) | Y^T f (10) | f^T f | n]
+__global__ void __launch_bounds__(128) k_gram_finalize(const double* __restrict__ partials, int nblocks, double n_samples, double* __restrict__ pack) {
+  __shared__ double tot[kAcc];
+  if (threadIdx.x < kAcc) {
+    double v = 0.0;
+    for (int b = 0; b < nblocks; ++b) v += partials[(int64_t)b * kAcc + threadIdx.x];  // fixed order
+    tot[threadIdx.x] = v;
+  }
+  __syncthreads();
+  auto tri = [](int n_, int i, int j) { if (i > j) { int t = i; i = j; j = t; } return i * n_ - i * (i - 1) / 2 + (j - i); };
+  const int t = threadIdx.x;
+  if (t < 100) {
+    const int a = t / 10, b = t % 10;
+    double v = 0.0;
+    if (a <= 3 && b <= 3) v += tot[tri(5, a, b)];
+    if (a >= 1 && b >= 1) v += tot[kTop + tri(10, a - 1, b - 1)];
+    pack[t] = v;
+  } else if (t < 110) {
+    const int a = t - 100;
+    double v = 0.0;
+    if (a <= 3) v += tot[tri(5, a, 4)];
+    if (a >= 1) v += tot[kTop + tri(10, a - 1, 9)];
+    pack[t] = v;
+  } else if (t == 110) {
+    pack[t] = tot[tri(5, 4, 4)] + tot[kTop + tri(10, 9, 9)];
+  } else if (t == 111) {
+    pack[t] = n_samples;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static int sm_count(int device) {
+  static int cached[64] = {0};
+  if (device >= 0 && device < 64 && cached[device]) return cached[device];
+  int v = 148;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+  if (device >= 0 && device < 64) cached[device] = v;
+  return v;
+}
+
+int gram_grid(const rbm_model* m, int64_t n) {
+  int64_t need = (n + kGramBlock - 1) / kGramBlock;
+  int64_t cap = sm_count(m->device);  // one 256-thread CTA per SM (register-limited), persistent
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+template <class T>
+int launch_regressor_rows(const T* tw, const T* dtw, T* Y, int64_t n, cudaStream_t st) {
+  if (n == 0) return RBM_OK;
+  k_regressor_rows<T><<<(unsigned)((n + kRowsBlock - 1) / kRowsBlock), kRowsBlock, 0, st>>>(tw, dtw, Y, n);
+  RBM_CUDA_TRY(cudaGetLastError());
+  return RBM_OK;
+}
+
+template <class T>
+int launch_sensor_twists(const double* pose_Rt, const T* tw, const T* dtw, T* tws, T* dtws, int64_t n, cudaStream_t st) {
+  if (n == 0) return RBM_OK;
+  PoseArg<T> p;
+  for (int k = 0; k < 9; ++k) p.R[k] = (T)pose_Rt[k];
+  for (int k = 0; k < 3; ++k) p.t[k] = (T)pose_Rt[9 + k];
+  k_sensor_twists<T><<<(unsigned)((n + kRowsBlock - 1) / kRowsBlock), kRowsBlock, 0, st>>>(p, tw, dtw, tws, dtws, n);
+  RBM_CUDA_TRY(cudaGetLastError());
+  return RBM_OK;
+}
+
+template <class T>
+int launch_regressor_from_traj(const rbm_model* m, const T* q, const T* qd, const T* qdd, T* Y, T* Vs, T* dVs, const T* phi, T* F, int64_t n, int64_t ld,
+                               cudaStream_t st) {
+  if (n == 0) return RBM_OK;
+  const unsigned grid = (unsigned)((n + kRowsBlock - 1) / kRowsBlock);
+  const int np = generic_param_count(m->nj);
+  const FastParams<T>& P = ModelView<T>::fast(m);
+  const T* gp = ModelView<T>::generic(m);
+  if (m->path == PATH_SEQ_ISO) k_regressor_from_traj<T, PATH_SEQ_ISO><<<grid, kRowsBlock, 0, st>>>(P, gp, m->nj, np, q, qd, qdd, Y, Vs, dVs, phi, F, n, ld);
+  else if (m->path == PATH_SEQ_RIGID) k_regressor_from_traj<T, PATH_SEQ_RIGID><<<grid, kRowsBlock, 0, st>>>(P, gp, m->nj, np, q, qd, qdd, Y, Vs, dVs, phi, F, n, ld);
+  else k_regressor_from_traj<T, PATH_GENERIC><<<grid, kRowsBlock, sizeof(T) * np, st>>>(P, gp, m->nj, np, q, qd, qdd, Y, Vs, dVs, phi, F, n, ld);
+  RBM_CUDA_TRY(cudaGetLastError());
+  return RBM_OK;
+}
+
+template <class T>
+int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* qdd, const T* f, double* pack, double* partials, int64_t n, int64_t ld,
+                          cudaStream_t st) {
+  const int grid = gram_grid(m, n);
+  const int np = generic_param_count(m->nj);
+  const FastParams<T>& P = ModelView<T>::fast(m);
+  const T* gp = ModelView<T>::generic(m);
+  if (n > 0) {
+    if (m->path == PATH_SEQ_ISO) k_regressor_gram<T, PATH_SEQ_ISO><<<grid, kGramBlock, 0, st>>>(P, gp, m->nj, np, q, qd, qdd, f, partials, n, ld);
+    else if (m->path == PATH_SEQ_RIGID) k_regressor_gram<T, PATH_SEQ_RIGID><<<grid, kGramBlock, 0, st>>>(P, gp, m->nj, np, q, qd, qdd, f, partials, n, ld);
+    else k_regressor_gram<T, PATH_GENERIC><<<grid, kGramBlock, sizeof(T) * np, st>>>(P, gp, m->nj, np, q, qd, qdd, f, partials, n, ld);
+    RBM_CUDA_TRY(cudaGetLastError());
+  }
+  k_gram_finalize<<<1, 128, 0, st>>>(partials, n > 0 ? grid : 0, (double)n, pack);
+  RBM_CUDA_TRY(cudaGetLastError());
+  return RBM_OK;
+}
+
+#define RBM_INST(T)                                                                                                                        \
+  template int launch_regressor_rows<T>(const T*, const T*, T*, int64_t, cudaStream_t);                                                    \
+  template int launch_sensor_twists<T>(const double*, const T*, const T*, T*, T*, int64_t, cudaStream_t);                                  \
+  template int launch_regressor_from_traj<T>(const rbm_model*, const T*, const T*, const T*, T*, T*, T*, const T*, T*, int64_t, int64_t, cudaStream_t); \
+  template int launch_regressor_gram<T>(const rbm_model*, const T*, const T*, const T*, const T*, double*, double*, int64_t, int64_t, cudaStream_t);
+RBM_INST(double)
+RBM_INST(float)
+
+}  // namespace rbm

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kBlock) k_rnea_generic_soa(const T* __restrict
     rqdd[j] = __ldg(qdd + j * ld + s);
   }
   T V[6], dV[6];
-  generic_rnea<T, NJ>(sp, nj, rq, rqd, rqdd, rtau, nullptr, nullptr, nullptr, V, dV);
+  generic_rnea<T, NJ>(sp, sp, nj, rq, rqd, rqdd, rtau, nullptr, nullptr, nullptr, V, dV);
 #pragma unroll
   for (int j = 0; j < njr; ++j) tau[j * ld + s] = rtau[j];
   if (Vout) {
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kBlock) k_rnea_generic_aos(const T* __restrict
   T rq[RBM_MAX_JOINTS], rqd[RBM_MAX_JOINTS], rqdd[RBM_MAX_JOINTS], rtau[RBM_MAX_JOINTS];
   const T* my = traj + s * 3 * nj;
   for (int j = 0; j < nj; ++j) { rq[j] = my[j]; rqd[j] = my[nj + j]; rqdd[j] = my[2 * nj + j]; }
-  generic_rnea<T, 0>(sp, nj, rq, rqd, rqdd, rtau, poses ? poses + s * nj * 12 : nullptr, twists ? twists + s * (nj + 1) * 6 : nullptr,
+  generic_rnea<T, 0>(sp, sp, nj, rq, rqd, rqdd, rtau, poses ? poses + s * nj * 12 : nullptr, twists ? twists + s * (nj + 1) * 6 : nullptr,
                      dtwists ? dtwists + s * (nj + 1) * 6 : nullptr, nullptr, nullptr);
   for (int j = 0; j < nj; ++j) tau[s * nj + j] = rtau[j];
 }

@@ -146,10 +146,9 @@ template <class T> RBM_HD void sincos_t(T x, T* s, T* c);
 template <> RBM_HD void sincos_t<double>(double x, double* s, double* c) { sincos(x, s, c); }
 template <> RBM_HD void sincos_t<float>(float x, float* s, float* c) { sincosf(x, s, c); }
 
-// Full RNEA for one sample.  WANT_TAU = false leaves the backward sweep out (regressor kernels).
-template <class T, class D, bool WANT_TAU>
-RBM_HD void fast_rnea(const FastParams<T>& P, const T (&q)[6], const T (&qd)[6], const T (&qdd)[6], FastResult<T>& out) {
-  T c[6], s[6];
+// sin / cos of the revolute joint angles of descriptor D (prismatic entries stay c = 1, s = 0)
+template <class T, class D>
+RBM_HD void fast_sincos(const T (&q)[6], T (&c)[6], T (&s)[6]) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) { c[i] = T(1); s[i] = T(0); }
   if constexpr (D::L0::jk == JOINT_RZ) sincos_t(q[0], &s[0], &c[0]);
@@ -158,11 +157,36 @@ RBM_HD void fast_rnea(const FastParams<T>& P, const T (&q)[6], const T (&qd)[6],
   if constexpr (D::L3::jk == JOINT_RZ) sincos_t(q[3], &s[3], &c[3]);
   if constexpr (D::L4::jk == JOINT_RZ) sincos_t(q[4], &s[4], &c[4]);
   if constexpr (D::L5::jk == JOINT_RZ) sincos_t(q[5], &s[5], &c[5]);
+}
 
+template <class T, class D, bool WANT_TAU>
+RBM_HD void fast_rnea_core(const FastParams<T>& P, const T* g, const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6],
+                           const T (&qdd)[6], FastResult<T>& out);
+
+// Joint sines / cosines supplied by the caller (the linearisation re-uses them across its many evaluations).
+template <class T, class D, bool WANT_TAU>
+RBM_HD void fast_rnea_cs(const FastParams<T>& P, const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6], const T (&qdd)[6],
+                         FastResult<T>& out) {
+  fast_rnea_core<T, D, WANT_TAU>(P, P.g, q, c, s, qd, qdd, out);
+}
+
+// Full RNEA for one sample.  WANT_TAU = false leaves the backward sweep out (regressor kernels).
+template <class T, class D, bool WANT_TAU>
+RBM_HD void fast_rnea(const FastParams<T>& P, const T (&q)[6], const T (&qd)[6], const T (&qdd)[6], FastResult<T>& out) {
+  T c[6], s[6];
+  fast_sincos<T, D>(q, c, s);
+  fast_rnea_cs<T, D, WANT_TAU>(P, q, c, s, qd, qdd, out);
+}
+
+// The recursion itself; `g` is the linear part of the base acceleration (P.g, or zeros when the joint-space inertia
+// matrix is being extracted column by column).
+template <class T, class D, bool WANT_TAU>
+RBM_HD void fast_rnea_core(const FastParams<T>& P, const T* g, const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6],
+                           const T (&qdd)[6], FastResult<T>& out) {
   // base: twist_0 = 0, dtwist_0 = [g; 0]  (core/simulate.py:149,154-155)
   auto v0 = Z3{};
   auto w0 = Z3{};
-  auto a0 = ld3(P.g);
+  auto a0 = ld3(g);
   auto l0 = Z3{};
   auto k0 = fwd_link<typename D::L0, 0>(P, q[0], qd[0], qdd[0], c[0], s[0], v0, w0, a0, l0);
   auto k1 = fwd_link<typename D::L1, 1>(P, q[1], qd[1], qdd[1], c[1], s[1], k0.v, k0.w, k0.a, k0.l);
@@ -278,7 +302,7 @@ RBM_HD void adjointT_apply(const T* R, G3<T> p, G3<T> f, G3<T> m, G3<T>& fo, G3<
 // survive until the backward sweep.  Optional full-state outputs mirror the reference's return value
 // (tau, poses, twists, dtwists) for the scalar drop-in API.
 template <class T, int NJ>
-__device__ __forceinline__ void generic_rnea(const T* __restrict__ sp, int nj_rt, const T* q, const T* qd, const T* qdd, T* tau,
+__device__ __forceinline__ void generic_rnea(const T* __restrict__ sp, const T* __restrict__ base /* [V0 | dV0 | Ftip], normally == sp */, int nj_rt, const T* q, const T* qd, const T* qdd, T* tau,
                                              T* poses /* [nj][12] or null */, T* twists /* [nj+1][6] or null */, T* dtwists /* idem */,
                                              T* Vlast /* [6] or null */, T* dVlast /* [6] or null */) {
   constexpr int MAXJ = NJ > 0 ? NJ : RBM_MAX_JOINTS;
@@ -286,8 +310,8 @@ __device__ __forceinline__ void generic_rnea(const T* __restrict__ sp, int nj_rt
   T Rs[MAXJ + 1][9];
   T ps[MAXJ + 1][3];
   T bs[MAXJ][6];
-  G3<T> v = g3(sp + GP_V0), w = g3(sp + GP_V0 + 3);
-  G3<T> a = g3(sp + GP_DV0), l = g3(sp + GP_DV0 + 3);
+  G3<T> v = g3(base + GP_V0), w = g3(base + GP_V0 + 3);
+  G3<T> a = g3(base + GP_DV0), l = g3(base + GP_DV0 + 3);
   if (twists) {
     twists[0] = v.x; twists[1] = v.y; twists[2] = v.z; twists[3] = w.x; twists[4] = w.y; twists[5] = w.z;
     dtwists[0] = a.x; dtwists[1] = a.y; dtwists[2] = a.z; dtwists[3] = l.x; dtwists[4] = l.y; dtwists[5] = l.z;
@@ -343,7 +367,7 @@ __device__ __forceinline__ void generic_rnea(const T* __restrict__ sp, int nj_rt
 #pragma unroll
   for (int k = 0; k < 9; ++k) Rs[nj][k] = sp[GP_TIPR + k];
   ps[nj][0] = sp[GP_TIPT]; ps[nj][1] = sp[GP_TIPT + 1]; ps[nj][2] = sp[GP_TIPT + 2];
-  G3<T> f = g3(sp + GP_FTIP), m = g3(sp + GP_FTIP + 3);
+  G3<T> f = g3(base + GP_FTIP), m = g3(base + GP_FTIP + 3);
 #pragma unroll
   for (int i = nj - 1; i >= 0; --i) {
     const T* J = sp + GP_HEAD + GJ_STRIDE * i;

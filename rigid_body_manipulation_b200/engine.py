@@ -178,3 +178,156 @@ class Model:
         rc = fn(self._h, _ptr(arr), _ptr(tau), n, int(chunk))
         _lib.check(rc, "rbm_rnea_host")
         return tau
+
+    # ---- sensor-frame regressor / identification --------------------------------------------------
+    def _check_soa(self, *ts):
+        self._check_dev(*ts)
+        q = ts[0]
+        if q.dim() != 2 or q.shape[0] != self.nj or q.dtype not in (torch.float64, torch.float32):
+            raise ValueError(f"q must be float64 / float32 with shape ({self.nj}, n)")
+        for t in ts[1:3]:
+            if t.shape != q.shape or t.dtype != q.dtype:
+                raise ValueError("q, qd, qdd must share shape and dtype")
+        return q.shape[1], q.dtype
+
+    def regressor_from_traj(self, q, qd, qdd, want_rows=True, want_twists=False, phi=None):
+        """(q, qd, qdd) (nj, n) -> dict with any of: Y (n, 6, 10), twist_sen / dtwist_sen (6, n), wrench (6, n) = Y phi."""
+        n, dt = self._check_soa(q, qd, qdd)
+        kw = dict(dtype=dt, device=q.device)
+        Y = torch.empty((n, 6, 10), **kw) if want_rows else None
+        Vs = torch.empty((6, n), **kw) if want_twists else None
+        dVs = torch.empty((6, n), **kw) if want_twists else None
+        ph = F = None
+        if phi is not None:
+            ph = torch.as_tensor(phi, **kw).contiguous()
+            if ph.shape != (10,):
+                raise ValueError("phi must hold the 10 inertial parameters")
+            F = torch.empty((6, n), **kw)
+        fn = self._lib.rbm_regressor_from_traj_f64 if dt == torch.float64 else self._lib.rbm_regressor_from_traj_f32
+        with torch.cuda.device(self.device):
+            rc = fn(self._h, _ptr(q), _ptr(qd), _ptr(qdd), _ptr(Y), _ptr(Vs), _ptr(dVs), _ptr(ph), _ptr(F), n, n, self._stream())
+        _lib.check(rc, "rbm_regressor_from_traj")
+        return dict(Y=Y, twist_sen=Vs, dtwist_sen=dVs, wrench=F)
+
+    def regressor_gram(self, q, qd, qdd, f, pack=None):
+        """Fused regressor + normal equations: returns the 112-double device pack [Y^T Y | Y^T f | f^T f | n]."""
+        n, dt = self._check_soa(q, qd, qdd)
+        self._check_dev(f, pack)
+        if f.shape != (6, n) or f.dtype != dt:
+            raise ValueError("f must have shape (6, n) and the dtype of q")
+        if pack is None:
+            pack = torch.empty(112, dtype=torch.float64, device=q.device)
+        elif pack.shape != (112,) or pack.dtype != torch.float64:
+            raise ValueError("pack must be a float64 tensor of 112 elements")
+        ws_bytes = int(self._lib.rbm_gram_workspace_bytes(self._h, n))
+        ws = getattr(self, "_gram_ws", None)
+        if ws is None or ws.numel() * 8 < ws_bytes:
+            ws = self._gram_ws = torch.empty(max(1, ws_bytes // 8), dtype=torch.float64, device=self.device)
+        fn = self._lib.rbm_regressor_gram_f64 if dt == torch.float64 else self._lib.rbm_regressor_gram_f32
+        with torch.cuda.device(self.device):
+            rc = fn(self._h, _ptr(q), _ptr(qd), _ptr(qdd), _ptr(f), _ptr(pack), _ptr(ws), ws.numel() * 8, n, n, self._stream())
+        _lib.check(rc, "rbm_regressor_gram")
+        return pack
+
+    # ---- LQR linearisation -----------------------------------------------------------------------------
+    def linearize(self, q, qd, u=None, dt=0.002, eps=1e-8, centered=True, want_qdd=False):
+        """States (q, qd) (nj, n) [+ ctrl u (nj, n)] -> A (n, 2nj, 2nj), B (n, 2nj, nj) as element-major VIEWS
+        (storage is [(r*cols + c)][n], so `A[s]` is a strided 2-D view; call .contiguous() for a packed copy)."""
+        self._check_dev(q, qd, u)
+        if q.dtype != torch.float64 or q.dim() != 2 or q.shape[0] != self.nj or qd.shape != q.shape or qd.dtype != q.dtype:
+            raise ValueError(f"q, qd must be float64 with shape ({self.nj}, n)")
+        if u is not None and (u.shape != q.shape or u.dtype != q.dtype):
+            raise ValueError("u must match q")
+        n, nj = q.shape[1], self.nj
+        A = torch.empty((2 * nj, 2 * nj, n), dtype=q.dtype, device=q.device)
+        B = torch.empty((2 * nj, nj, n), dtype=q.dtype, device=q.device)
+        qdd = torch.empty_like(q) if want_qdd else None
+        with torch.cuda.device(self.device):
+            rc = self._lib.rbm_linearize_f64(self._h, _ptr(q), _ptr(qd), _ptr(u), float(dt), float(eps), int(bool(centered)), _ptr(A), _ptr(B),
+                                             _ptr(qdd), n, n, self._stream())
+        _lib.check(rc, "rbm_linearize")
+        out = (A.permute(2, 0, 1), B.permute(2, 0, 1))
+        return out + (qdd,) if want_qdd else out
+
+
+# ---- model-free batched helpers (device tensors in, device tensors out) ------------------------------------
+def _dev64(x, shape_tail):
+    t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float64))
+    t = t.to(device="cuda", dtype=torch.float64).contiguous()
+    if tuple(t.shape[1:]) != tuple(shape_tail):
+        raise ValueError(f"expected trailing shape {tuple(shape_tail)}, got {tuple(t.shape[1:])}")
+    return t
+
+
+def _cur_stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def regressor_rows(twists, dtwists):
+    """get_regressor_matrix batched: (n, 6), (n, 6) -> (n, 6, 10) on the device."""
+    tw, dtw = _dev64(twists, (6,)), _dev64(dtwists, (6,))
+    if tw.shape != dtw.shape:
+        raise ValueError("twists and dtwists must have the same shape")
+    Y = torch.empty((tw.shape[0], 6, 10), dtype=torch.float64, device=tw.device)
+    _lib.check(_lib.load().rbm_regressor_rows_f64(_ptr(tw), _ptr(dtw), _ptr(Y), tw.shape[0], _cur_stream()), "rbm_regressor_rows")
+    return Y
+
+
+def sensor_twists(pose, twists, dtwists):
+    """core/simulate.py:202-209 batched: V_s = Ad(T) V, dV_s = Ad(T) dV."""
+    Rt = pose_to_Rt(pose)
+    tw, dtw = _dev64(twists, (6,)), _dev64(dtwists, (6,))
+    o1, o2 = torch.empty_like(tw), torch.empty_like(dtw)
+    _lib.check(_lib.load().rbm_sensor_twists_f64(_ptr(Rt), _ptr(tw), _ptr(dtw), _ptr(o1), _ptr(o2), tw.shape[0], _cur_stream()), "rbm_sensor_twists")
+    return o1, o2
+
+
+def transfer_simat(poses_Rt, simats, adjoint_form=False):
+    """transfer_simat (default) or coordinate_transfer_simat (adjoint_form=True), batched: (n,12), (n,6,6) -> (n,6,6)."""
+    P, G = _dev64(poses_Rt, (12,)), _dev64(simats, (6, 6))
+    if P.shape[0] != G.shape[0]:
+        raise ValueError("The numbers of spatial inertia tensors and SE3 instances do not match.")
+    out = torch.empty_like(G)
+    lib = _lib.load()
+    fn = lib.rbm_coordinate_transfer_simat_f64 if adjoint_form else lib.rbm_transfer_simat_f64
+    _lib.check(fn(_ptr(P), _ptr(G), _ptr(out), P.shape[0], _cur_stream()), "rbm_transfer_simat")
+    return out
+
+
+def coordinate_transfer_imat(poses_Rt, imats, mass):
+    P, I = _dev64(poses_Rt, (12,)), _dev64(imats, (3, 3))
+    m = _dev64(np.atleast_1d(mass) if not isinstance(mass, torch.Tensor) else mass, ())
+    out = torch.empty_like(I)
+    _lib.check(_lib.load().rbm_coordinate_transfer_imat_f64(_ptr(P), _ptr(I), _ptr(m), _ptr(out), P.shape[0], _cur_stream()), "rbm_coordinate_transfer_imat")
+    return out
+
+
+def spatial_inertia(mass, diag):
+    m = _dev64(np.atleast_1d(mass) if not isinstance(mass, torch.Tensor) else mass, ())
+    d = _dev64(diag, (3,))
+    if m.shape[0] != d.shape[0]:
+        raise ValueError("Lenght of 'mass' of the bodies and that of 'diagonal_inertia' vectors must match.")
+    out = torch.empty((m.shape[0], 6, 6), dtype=torch.float64, device=m.device)
+    _lib.check(_lib.load().rbm_spatial_inertia_f64(_ptr(m), _ptr(d), _ptr(out), m.shape[0], _cur_stream()), "rbm_spatial_inertia")
+    return out
+
+
+def compose_poses(trans, rot):
+    """(n,3) + (n,4) wxyz quaternions or (n,9) rotation matrices -> poses (n,12) and an int32 status vector."""
+    rot_t = rot if isinstance(rot, torch.Tensor) else torch.as_tensor(np.asarray(rot, dtype=np.float64))
+    rot_len = int(rot_t.shape[1])
+    t, r = _dev64(trans, (3,)), _dev64(rot_t, (rot_len,))
+    out = torch.empty((t.shape[0], 12), dtype=torch.float64, device=t.device)
+    status = torch.empty((t.shape[0],), dtype=torch.int32, device=t.device)
+    _lib.check(_lib.load().rbm_compose_f64(_ptr(t), _ptr(r), rot_len, _ptr(out), _ptr(status), t.shape[0], _cur_stream()), "rbm_compose")
+    return out, status
+
+
+def point_motion(twists, dtwists, points, want_acc=True):
+    """extract_linvel / extract_linacc_frame_transferred batched -> (linvel (n,3), linacc (n,3) or None)."""
+    tw, p = _dev64(twists, (6,)), _dev64(points, (3,))
+    dtw = _dev64(dtwists, (6,)) if (want_acc and dtwists is not None) else None
+    lv = torch.empty_like(p)
+    la = torch.empty_like(p) if dtw is not None else None
+    _lib.check(_lib.load().rbm_point_motion_f64(_ptr(tw), _ptr(dtw), _ptr(p), _ptr(lv), _ptr(la), p.shape[0], _cur_stream()), "rbm_point_motion")
+    return lv, la

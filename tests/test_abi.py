@@ -1,0 +1,69 @@
+"""`not gpu`: the C-ABI library builds, loads and exports every symbol include/rbm_b200.h declares; the ctypes
+signature table covers exactly those symbols; argument validation that needs no device works; and the product package
+never reaches into oracle/."""
+import ctypes as C
+import os
+import re
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from rigid_body_manipulation_b200 import _lib
+
+    lib = _lib.load()
+    declared = _lib.header_symbols()
+    assert len(declared) >= 28 and len(set(declared)) == len(declared)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in rbm_b200.h but not exported"
+    assert set(declared) == set(_lib.SIGNATURES), set(declared) ^ set(_lib.SIGNATURES)
+    assert lib.rbm_version().decode().startswith("rbm_b200")
+
+
+def test_header_cites_the_reference_for_every_compute_entry_point():
+    text = open(os.path.join(ROOT, "include", "rbm_b200.h")).read()
+    for fn in ["dynamics/dynamics.py:109-157", "dynamics/dynamics.py:72-106", "dynamics/dynamics.py:215-249", "core/simulate.py:202-209",
+               "loggers/loggers.py:127-129", "dynamics/dynamics.py:41-46", "transformations/transformations.py:8-50", "dynamics.py:160-212"]:
+        assert fn in text, fn
+
+
+def test_argument_validation_without_a_device():
+    from rigid_body_manipulation_b200 import _lib
+
+    lib = _lib.load()
+    out = C.c_void_p()
+    assert lib.rbm_model_create(0, None, None, None, None, None, None, None, None, 0, 0, C.byref(out)) == _lib.RBM_ERR_INVALID
+    assert b"nj" in lib.rbm_last_error_string()
+    assert lib.rbm_model_create(17, None, None, None, None, None, None, None, None, 0, 0, C.byref(out)) == _lib.RBM_ERR_UNSUPPORTED
+    assert lib.rbm_rnea_f64(None, None, None, None, None, None, None, 4, 4, None) == _lib.RBM_ERR_INVALID
+    assert lib.rbm_compose_f64(None, None, 5, None, None, 1, None) == _lib.RBM_ERR_INVALID
+    assert lib.rbm_model_num_joints(None) == _lib.RBM_ERR_INVALID
+
+
+def test_no_silent_cpu_path():
+    """Without a CUDA device model creation must fail loudly (RbmCudaError), never compute on the host."""
+    import numpy as np
+    import pytest
+    import torch
+
+    from rigid_body_manipulation_b200 import _lib, model
+    from rigid_body_manipulation_b200.engine import Model
+
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    c = model.load_packaged("sequential", "hammer")
+    with pytest.raises(_lib.RbmCudaError):
+        Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0)
+    assert _lib.load().rbm_device_count() == 0
+    assert np.isfinite(c.simats).all()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "rigid_body_manipulation_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src), f"{f} imports the oracle"
+                assert "/root/reference" not in src or f in ("extract_reference_assets.py",), f

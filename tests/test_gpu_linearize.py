@@ -1,0 +1,100 @@
+"""-m gpu parity of the batched LQR linearisation (rbm_linearize_f64) against the literal CPU restatement of
+mjd_transitionFD on the same plant (oracle/lqr_oracle.py; reference dynamics/dynamics.py:41-46, controllers/lqr.py:43-49)."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import load_golden, model_from_golden, sample_states
+from oracle import lqr_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+
+def consts_of(g):
+    return dict(hposes_Rt=g["hposes_Rt"], simats=g["simats"], uscrews=g["uscrews"], twist_0=g["twist_0"], dtwist_0=g["dtwist_0"])
+
+
+def run(m, q, qd, u, **kw):
+    to = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a.T), device="cuda")
+    A, B, qdd = m.linearize(to(q), to(qd), to(u), want_qdd=True, **kw)
+    torch.cuda.synchronize()
+    return A.cpu().numpy(), B.cpu().numpy(), qdd.t().cpu().numpy()
+
+
+@pytest.mark.parametrize("fname", ["ref_inverse_hammer.npz", "ref_inverse_kill_la_kill.npz"])
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_matches_transition_fd_oracle(fname, force_generic):
+    g = load_golden(fname)
+    m = model_from_golden(g, force_generic=force_generic)
+    n = 48
+    tr = sample_states(np.random.default_rng(3), n)
+    q, qd = tr[:, 0], tr[:, 1]
+    u = np.random.default_rng(4).standard_normal((n, 6)) * np.array([100, 100, 400, 1, 1, 1.0])
+    c = consts_of(g)
+    # (a) a well-conditioned step: truncation O(eps^2), round-off O(1e-16/eps) -> both sides agree tightly
+    A, B, qdd = run(m, q, qd, u, dt=0.002, eps=1e-5, centered=True)
+    Ar, Br = lo.transition_fd(c, q, qd, u, dt=0.002, eps=1e-5, centered=True)
+    assert np.abs(qdd - lo.forward_dynamics(c, q, qd, u)).max() < 1e-9 * np.abs(qdd).max()
+    assert np.abs(A - Ar).max() < 2e-8
+    assert np.abs(B - Br).max() < 2e-8
+    # (b) the reference's own defaults (StateSpaceConfig: eps 1e-8, centred): both sides carry ~1e-7 FD round-off
+    A, B, _ = run(m, q, qd, u, dt=0.002, eps=1e-8, centered=True)
+    Ar, Br = lo.transition_fd(c, q, qd, u, dt=0.002, eps=1e-8, centered=True)
+    assert np.abs(A - Ar).max() < 5e-6
+    assert np.abs(B - Br).max() < 5e-6
+    # (c) forward differences
+    A, B, _ = run(m, q, qd, u, dt=0.002, eps=1e-6, centered=False)
+    Ar, Br = lo.transition_fd(c, q, qd, u, dt=0.002, eps=1e-6, centered=False)
+    assert np.abs(A - Ar).max() < 1e-4  # first-order truncation differs between differentiating ID and FD of the step
+    assert np.abs(B - Br).max() < 2e-7
+
+
+def test_structure_of_the_euler_map():
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    n, dt = 1000, 0.002
+    tr = sample_states(np.random.default_rng(9), n)
+    A, B, _ = run(m, tr[:, 0], tr[:, 1], None, dt=dt, eps=1e-6)
+    Minv = lo.mass_matrix(consts_of(g), tr[:, 0])
+    Minv = np.linalg.inv(Minv)
+    assert np.abs(B[:, 6:, :] - dt * Minv).max() < 1e-12
+    assert np.abs(B[:, :6, :] - dt * dt * Minv).max() < 1e-14
+    # q+ = q + dt qd+  =>  top block rows are dt * bottom rows + [I 0]
+    I = np.eye(6)
+    assert np.abs(A[:, :6, :6] - (I + dt * A[:, 6:, :6])).max() < 1e-12
+    assert np.abs(A[:, :6, 6:] - dt * A[:, 6:, 6:]).max() < 1e-12
+    # prismatic gantry: translations do not change the dynamics -> d qdd / d q_{0..2} == 0
+    assert np.abs(A[:, 6:, :3]).max() < 1e-6
+
+
+def test_keyframe_linearisation_feeds_lqr():
+    """The reference's actual use (controllers/lqr.py:34-49): one linearisation at the keyframe at rest, then DARE -> K."""
+    from scipy import linalg
+
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    q = g["key_qpos"][None]
+    A, B, _ = run(m, q, np.zeros((1, 6)), None, dt=0.002, eps=1e-8)
+    Ar, Br = lo.transition_fd(consts_of(g), q, np.zeros((1, 6)), None, dt=0.002, eps=1e-8)
+    R = np.diag([10.0, 10, 10, 1e4, 1e4, 1e4])  # configurations/base.yaml:33-39
+
+    def gain(A, B):
+        P = linalg.solve_discrete_are(A, B, np.eye(12), R)
+        return linalg.pinv(R + B.T @ P @ B) @ B.T @ P @ A
+
+    K, Kr = gain(A[0], B[0]), gain(Ar[0], Br[0])
+    assert np.abs(K - Kr).max() < 1e-4 * np.abs(Kr).max()
+
+
+def test_one_million_states_runs_and_is_consistent():
+    """BASELINE.json config 4 size: 2^20 states; spot-check 64 of them against the oracle."""
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    n = 1 << 20
+    tr = sample_states(np.random.default_rng(17), n)
+    A, B, _ = run(m, tr[:, 0], tr[:, 1], None, dt=0.002, eps=1e-6)
+    idx = np.random.default_rng(1).choice(n, 64, replace=False)
+    Ar, Br = lo.transition_fd(consts_of(g), tr[idx, 0], tr[idx, 1], None, dt=0.002, eps=1e-6)
+    assert np.abs(A[idx] - Ar).max() < 5e-8
+    assert np.abs(B[idx] - Br).max() < 5e-8
+    assert np.isfinite(A).all() and np.isfinite(B).all()

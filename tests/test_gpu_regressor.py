@@ -1,0 +1,135 @@
+"""-m gpu parity of the sensor-frame regressor, the fused Gram accumulation and the identification they feed
+(reference core/simulate.py:202-224, dynamics/dynamics.py:215-249, loggers/loggers.py:127-129)."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import load_golden, model_from_golden, rel_err, sample_states, soa
+from oracle import rnea_vec as rv
+from rigid_body_manipulation_b200 import engine, identification
+
+pytestmark = pytest.mark.gpu
+ALL = ["ref_inverse_hammer.npz", "ref_inverse_uniform_gearbox.npz", "ref_inverse_kill_la_kill.npz", "ref_inverse_generic_nj6.npz",
+       "ref_inverse_generic_nj4.npz", "ref_inverse_generic_nj9.npz"]
+
+
+@pytest.mark.parametrize("fname", ALL)
+def test_regressor_rows_and_sensor_twists_from_given_twists(fname):
+    g = load_golden(fname)
+    nj = g["uscrews"].shape[0]
+    Vs, dVs = engine.sensor_twists(g["pose_sen_llj"], g["twists"][:, nj], g["dtwists"][:, nj])
+    assert rel_err(Vs.cpu().numpy(), g["twist_sen"]).max() < 1e-12
+    assert rel_err(dVs.cpu().numpy(), g["dtwist_sen"]).max() < 1e-12
+    Y = engine.regressor_rows(g["twist_sen"], g["dtwist_sen"])
+    assert rel_err(Y.cpu().numpy(), g["regressor"]).max() < 1e-13
+
+
+@pytest.mark.parametrize("fname", ALL)
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_fused_regressor_from_trajectory(fname, force_generic):
+    g = load_golden(fname)
+    m = model_from_golden(g, force_generic=force_generic)
+    q, qd, qdd = soa(g["traj"])
+    phi = np.array([1.3, 0.1, -0.2, 0.3, 0.02, 0.03, 0.04, 0.001, -0.002, 0.003])
+    out = m.regressor_from_traj(q, qd, qdd, want_rows=True, want_twists=True, phi=phi)
+    assert rel_err(out["twist_sen"].t().cpu().numpy(), g["twist_sen"]).max() < 1e-9
+    assert rel_err(out["dtwist_sen"].t().cpu().numpy(), g["dtwist_sen"]).max() < 1e-9
+    assert rel_err(out["Y"].cpu().numpy(), g["regressor"]).max() < 1e-9
+    assert rel_err(out["wrench"].t().cpu().numpy(), g["regressor"] @ phi).max() < 1e-9
+    # fp32 mode
+    q32, qd32, qdd32 = soa(g["traj"], torch.float32)
+    o32 = m.regressor_from_traj(q32, qd32, qdd32)
+    assert rel_err(o32["Y"].cpu().numpy(), g["regressor"]).max() < 1e-4
+
+
+def _gram_reference(g, traj, f):
+    nj = g["uscrews"].shape[0]
+    kw = dict(wrench_tip=g["wrench_tip"], pose_tip_Rt=g["pose_tip"]) if "wrench_tip" in g.files else {}
+    out = rv.inverse_batched(traj, g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"], **kw)
+    Vs, dVs = rv.sensor_frame_twists_batched(g["pose_sen_llj"], out["twists"][:, nj], out["dtwists"][:, nj])
+    Y = rv.regressor_batched(Vs, dVs)
+    return Y, rv.gram_pack(Y, f)
+
+
+@pytest.mark.parametrize("fname", ["ref_inverse_hammer.npz", "ref_inverse_generic_nj6.npz", "ref_inverse_generic_nj9.npz"])
+@pytest.mark.parametrize("n", [1, 255, 4096, 100_003])
+def test_gram_matches_materialised_normal_equations(fname, n):
+    g = load_golden(fname)
+    m = model_from_golden(g)
+    nj = m.nj
+    rng = np.random.default_rng(n)
+    traj = sample_states(rng, n) if nj == 6 else np.stack([rng.uniform(-3, 3, (n, nj)), rng.standard_normal((n, nj)), rng.standard_normal((n, nj))], 1)
+    f = rng.standard_normal((n, 6)) * np.array([5, 5, 5, 1, 1, 1.0])
+    Y, ref = _gram_reference(g, traj, f)
+    q, qd, qdd = soa(traj)
+    fd = torch.as_tensor(f, device="cuda").t().contiguous()
+    pack = m.regressor_gram(q, qd, qdd, fd).cpu().numpy()
+    scale = np.abs(ref[:100]).max()
+    assert np.abs(pack[:100] - ref[:100]).max() < 1e-9 * scale
+    assert np.abs(pack[100:110] - ref[100:110]).max() < 1e-9 * max(np.abs(ref[100:110]).max(), 1.0)
+    assert abs(pack[110] - ref[110]) < 1e-9 * ref[110]
+    assert pack[111] == n
+    # bit-reproducible (fixed reduction order, no atomics)
+    assert np.array_equal(pack, m.regressor_gram(q, qd, qdd, fd).cpu().numpy())
+    # symmetric by construction
+    G = pack[:100].reshape(10, 10)
+    assert np.array_equal(G, G.T)
+
+
+def test_gram_empty_batch():
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    e = torch.empty((6, 0), dtype=torch.float64, device="cuda")
+    pack = m.regressor_gram(e, e, e, e).cpu().numpy()
+    assert not pack.any()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 2e-3)])
+def test_identification_recovers_object_parameters(dtype, tol):
+    """Exact-recovery property at scale (config-3 shaped, one shard): f = Y phi_true synthesised on the device, Gram
+    accumulated over 2^21 samples, 10x10 solve on the host -> phi_true; and agreement with np.linalg.lstsq on a subset."""
+    g = load_golden("ref_inverse_uniform_gearbox.npz")
+    m = model_from_golden(g)
+    n = 1 << 21
+    rng = np.random.default_rng(42)
+    traj = sample_states(rng, n)
+    q, qd, qdd = soa(traj, dtype)
+    phi_true = np.array([0.585, -0.0032, 1.9e-5, -8e-6, 3.85e-4, 2.9e-4, 3.0e-4, 1e-6, 2e-6, -1e-6]) * np.array([1, 1, 1, 1, 10, 10, 10, 10, 10, 10])
+    f = m.regressor_from_traj(q, qd, qdd, want_rows=False, phi=phi_true)["wrench"]
+    ident = identification.solve(m.regressor_gram(q, qd, qdd, f))
+    assert ident.n_samples == n and ident.rank == 10
+    err = np.abs(ident.phi - phi_true) / np.array([1, 1e-2, 1e-2, 1e-2, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3])
+    assert err.max() < tol, (ident.phi, phi_true)
+    if dtype == torch.float64:
+        assert ident.rms_residual < 1e-9
+        sub = 20000
+        out = rv.inverse_batched(traj[:sub], g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"])
+        Vs, dVs = rv.sensor_frame_twists_batched(g["pose_sen_llj"], out["twists"][:, 6], out["dtwists"][:, 6])
+        Y = rv.regressor_batched(Vs, dVs)
+        noise = np.random.default_rng(0).standard_normal((sub, 6)) * 0.05
+        fn = Y @ phi_true + noise
+        ref = rv.identify_lstsq(Y, fn)  # the reference's solver (loggers.py:129)
+        fd = torch.as_tensor(fn, device="cuda").t().contiguous()
+        got = identification.solve(m.regressor_gram(q[:, :sub].contiguous(), qd[:, :sub].contiguous(), qdd[:, :sub].contiguous(), fd))
+        assert np.abs(got.phi - ref).max() < 1e-9 * max(1.0, got.cond ** 0.5)
+
+
+def test_gram_linearity_checksum_at_full_size():
+    """Size-independent property at config-3 per-rank size (1.25e7 samples): the pack is additive over a split of the batch."""
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    n = 12_500_000
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    q = torch.empty((6, n), dtype=torch.float64, device="cuda")
+    q[:3] = torch.rand((3, n), generator=gen, device="cuda", dtype=torch.float64) * 4 - 1.5
+    q[3:] = (torch.rand((3, n), generator=gen, device="cuda", dtype=torch.float64) * 2 - 1) * 6 * np.pi
+    qd = torch.randn((6, n), generator=gen, device="cuda", dtype=torch.float64)
+    qdd = torch.randn((6, n), generator=gen, device="cuda", dtype=torch.float64) * 3
+    f = torch.randn((6, n), generator=gen, device="cuda", dtype=torch.float64)
+    whole = m.regressor_gram(q, qd, qdd, f).clone()
+    cut = 5_000_011
+    a = m.regressor_gram(q[:, :cut].contiguous(), qd[:, :cut].contiguous(), qdd[:, :cut].contiguous(), f[:, :cut].contiguous()).clone()
+    b = m.regressor_gram(q[:, cut:].contiguous(), qd[:, cut:].contiguous(), qdd[:, cut:].contiguous(), f[:, cut:].contiguous()).clone()
+    diff = (whole - (a + b)).abs().max().item()
+    assert diff < 1e-10 * whole.abs().max().item()
+    assert whole[111].item() == n
