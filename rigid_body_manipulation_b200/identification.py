@@ -21,7 +21,8 @@ PARAM_LABELS = ["total_mass", "mx", "my", "mz", "ixx", "iyy", "izz", "ixy", "iyz
 class Identification:
     phi: np.ndarray          # (10,)
     n_samples: float
-    residual_ss: float       # ||Y phi - f||^2 from the normal equations
+    residual_ss: float       # ||Y phi - f||^2 from the normal equations (cancellation-limited: ~1e-16 * f_ss)
+    f_ss: float              # ||f||^2
     rms_residual: float      # per scalar wrench component
     cond: float              # condition number of the column-scaled Gram
     rank: int
@@ -49,7 +50,7 @@ def solve(pack, rcond: float = 1e-13) -> Identification:
     phi = z / d
     rss = max(ff - 2.0 * phi @ b + phi @ G @ phi, 0.0)
     cond = float(w.max() / w[keep].min()) if keep.any() else float("inf")
-    return Identification(phi=phi, n_samples=n, residual_ss=rss, rms_residual=float(np.sqrt(rss / max(6.0 * n, 1.0))), cond=cond, rank=int(keep.sum()))
+    return Identification(phi=phi, n_samples=n, residual_ss=rss, f_ss=ff, rms_residual=float(np.sqrt(rss / max(6.0 * n, 1.0))), cond=cond, rank=int(keep.sum()))
 
 
 def score(estimate, gt_params, aabb_scale: float) -> float:
