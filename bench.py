@@ -142,6 +142,9 @@ def consts_dict(c):
 
 
 def run_reference_arm(args):
+    """The reference's CPU algorithm for the path (per-sample oracle port; the reference itself is Python + an absent
+    third-party dependency and cannot travel to the GPU box) on every host core, same metric / config as the GPU arm.
+    Each step is a bounded sample of the workload, sized from a short calibration so the run ends within ~2 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -150,11 +153,13 @@ def run_reference_arm(args):
     c = load_constants()
     consts = consts_dict(c)
     cores = os.cpu_count() or 1
-    per_step = args.cpu_samples if args.cpu_samples > 0 else 2000 * cores
     pool = mp.get_context("fork").Pool(cores)
     try:
+        rate, _, _ = cpu_reference_rate(consts, cores * 100, cores, pool)  # calibration (also warms the workers)
+        budget_s = 90.0
+        per_step = args.cpu_samples if args.cpu_samples > 0 else int(max(cores * 20, min(rate * budget_s / max(args.steps + args.warmup, 1), 4000 * cores)))
         for _ in range(args.warmup):
-            cpu_reference_rate(consts, max(cores * 50, per_step // 10), cores, pool)
+            cpu_reference_rate(consts, per_step, cores, pool)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             cpu_reference_rate(consts, per_step, cores, pool)
@@ -178,6 +183,133 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
+L2_BYTES = 126e6
+
+
+class RneaWorkload:
+    """configs[1] (and, with --dtype f32 / --samples, the configs[4] sweep): tau for B resident samples."""
+    metric, unit = METRIC, UNIT
+    launches_per_step = 1
+
+    def __init__(self, args, model, rank, torch):
+        self.torch, self.model, self.B = torch, model, args.samples
+        self.esize = 8 if args.dtype == "f64" else 4
+        self.tdt = torch.float64 if args.dtype == "f64" else torch.float32
+        self.alg_bytes = 24 * self.esize * self.B  # SURVEY.md 8(d): 18 scalars read + 6 written per sample
+        self.workload = WORKLOAD if (self.B == 1 << 20 and args.dtype == "f64") else f"batched inverse dynamics, {self.B} synthetic samples, {args.dtype}, base.yaml manipulator + hammer"
+        host = sample_states(np.random.default_rng(1000 + rank), self.B).astype(np.float64 if args.dtype == "f64" else np.float32)
+        self.traj_pinned = torch.as_tensor(host).pin_memory()
+        # L2 rule: rotate over enough independent buffer sets that the data touched between two uses of one set
+        # exceeds 3x the 126 MB L2, so no timed launch can be served from cache
+        self.nset = max(2, int(np.ceil(3 * L2_BYTES / self.alg_bytes)) + 1)
+        dev = torch.as_tensor(host, device="cuda")
+        self.sets = []
+        for i in range(self.nset):
+            q, qd, qdd = (dev[:, k, :].t().contiguous() for k in range(3))
+            if i:  # distinct values per set, same distribution
+                q, qd, qdd = q + 1e-3 * i, qd * (1 + 1e-3 * i), qdd * (1 - 1e-3 * i)
+            self.sets.append((q, qd, qdd, torch.empty_like(q)))
+        del dev
+        self.k = 0
+        self.tau_host = torch.empty((self.B, 6), dtype=self.tdt).pin_memory()
+        self.layout = "SoA [3][6][B] resident in HBM"
+        self.h2d, self.d2h = 18 * self.esize * self.B, 6 * self.esize * self.B
+        self.e2e_api = "Model.rnea_host -> rbm_rnea_host_* (pinned host AoS traj in, pinned host tau out, chunked 3-stream pipeline)"
+
+    def step(self):
+        q, qd, qdd, tau = self.sets[self.k % self.nset]
+        self.k += 1
+        self.model.rnea(q, qd, qdd, tau=tau)
+
+    def e2e_step(self):
+        self.model.rnea_host(self.traj_pinned, tau=self.tau_host)
+
+
+class GramWorkload:
+    """configs[2] per-rank share: fused sensor-frame regressor + Gram of B samples (+ one 112-double all-reduce when N > 1)."""
+    metric, unit = "regressor_gram_samples_per_s", "samples/s"
+    launches_per_step = 2  # accumulate + finalize
+
+    def __init__(self, args, model, rank, torch):
+        from rigid_body_manipulation_b200 import distributed
+
+        self.torch, self.model, self.B, self.dist = torch, model, args.samples, distributed
+        self.esize = 8 if args.dtype == "f64" else 4
+        self.tdt = torch.float64 if args.dtype == "f64" else torch.float32
+        self.alg_bytes = 24 * self.esize * self.B  # q, qd, qdd, f read; nothing written per sample
+        self.workload = f"configs[2] per-GPU share: regressor + Y^T Y / Y^T f Gram over {self.B} synthetic samples, {args.dtype}"
+        gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        B = self.B
+        self.nset = max(2, int(np.ceil(3 * L2_BYTES / self.alg_bytes)) + 1)
+        phi = np.array([0.585, -0.0032, 1.9e-5, -8e-6, 3.85e-3, 2.9e-3, 3.0e-3, 1e-5, 2e-5, -1e-5])
+        self.sets = []
+        for _ in range(self.nset):
+            q = torch.empty((6, B), dtype=self.tdt, device="cuda")
+            q[:3] = torch.rand((3, B), generator=gen, device="cuda", dtype=self.tdt) * 4 - 1.5
+            q[3:] = (torch.rand((3, B), generator=gen, device="cuda", dtype=self.tdt) * 2 - 1) * (6 * np.pi)
+            qd = torch.randn((6, B), generator=gen, device="cuda", dtype=self.tdt)
+            qd[3:] *= 3
+            qdd = torch.randn((6, B), generator=gen, device="cuda", dtype=self.tdt) * 3
+            qdd[3:] *= 3.3333
+            f = model.regressor_from_traj(q, qd, qdd, want_rows=False, phi=phi)["wrench"]
+            self.sets.append((q, qd, qdd, f))
+        self.pack = torch.empty(112, dtype=torch.float64, device="cuda")
+        self.k = 0
+        self.layout = "SoA q,qd,qdd,f [6][B] resident in HBM"
+        self.host = [t.cpu().pin_memory() for t in self.sets[0]]
+        self.stage = [torch.empty_like(t) for t in self.sets[0]]
+        self.h2d, self.d2h = 24 * self.esize * B, 112 * 8
+        self.e2e_api = "pinned host q,qd,qdd,f -> cudaMemcpyAsync -> Model.regressor_gram -> pack.cpu()"
+
+    def step(self):
+        q, qd, qdd, f = self.sets[self.k % self.nset]
+        self.k += 1
+        self.model.regressor_gram(q, qd, qdd, f, pack=self.pack)
+        self.dist.allreduce_gram(self.pack)
+
+    def e2e_step(self):
+        for h, d in zip(self.host, self.stage):
+            d.copy_(h, non_blocking=True)
+        self.model.regressor_gram(*self.stage, pack=self.pack)
+        self.dist.allreduce_gram(self.pack)
+        return self.pack.cpu()
+
+
+class LinearizeWorkload:
+    """configs[3]: A (12x12), B (12x6) of the discrete transition at B joint states (RNEA-based finite differences)."""
+    metric, unit = "lqr_linearizations_per_s", "states/s"
+    launches_per_step = 1
+
+    def __init__(self, args, model, rank, torch):
+        self.torch, self.model, self.B = torch, model, args.samples
+        self.esize, self.tdt = 8, torch.float64
+        self.alg_bytes = 228 * 8 * self.B  # 12 scalars read, 144 + 72 written per state (SURVEY.md 8(d))
+        self.workload = f"configs[3]: LQR linearisation (A 12x12, B 12x6) at {self.B} joint states, centred FD eps 1e-8, dt 0.002, f64"
+        host = sample_states(np.random.default_rng(2000 + rank), self.B)
+        dev = torch.as_tensor(host, device="cuda")
+        self.q, self.qd = dev[:, 0, :].t().contiguous(), dev[:, 1, :].t().contiguous()
+        self.qh, self.qdh = self.q.cpu().pin_memory(), self.qd.cpu().pin_memory()
+        self.nset = 1
+        self.layout = "SoA q,qd [6][B] in; element-major A [144][B], B [72][B] out (output alone is 1.7 KB/state >> L2 for B = 2^20)"
+        self.h2d, self.d2h = 12 * 8 * self.B, 216 * 8 * self.B
+        self.e2e_api = "pinned host q,qd -> Model.linearize -> A,B copied to pinned host"
+        self.Ah = torch.empty((12, 12, self.B), dtype=self.tdt).pin_memory()
+        self.Bh = torch.empty((12, 6, self.B), dtype=self.tdt).pin_memory()
+
+    def step(self):
+        self.out = self.model.linearize(self.q, self.qd, None, dt=0.002, eps=1e-8, centered=True)
+
+    def e2e_step(self):
+        q, qd = self.qh.cuda(non_blocking=True), self.qdh.cuda(non_blocking=True)
+        A, Bm = self.model.linearize(q, qd, None, dt=0.002, eps=1e-8, centered=True)
+        self.Ah.copy_(A.permute(1, 2, 0), non_blocking=True)
+        self.Bh.copy_(Bm.permute(1, 2, 0), non_blocking=True)
+        self.torch.cuda.synchronize()
+
+
+WORKLOADS = {"rnea": RneaWorkload, "gram": GramWorkload, "linearize": LinearizeWorkload}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -195,29 +327,8 @@ def run_gpu_arm(args):
 
     c = load_constants()
     model = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, pose_sen_llj=c.pose_sen_Rt, device=local)
-    tdt = torch.float64 if args.dtype == "f64" else torch.float32
-    B = args.samples
-    traj_host = sample_states(np.random.default_rng(1000 + rank), B).astype(np.float64 if args.dtype == "f64" else np.float32)
-    traj_pinned = torch.as_tensor(traj_host).pin_memory()
-    esize = 8 if args.dtype == "f64" else 4
-    alg_bytes = 24 * esize * B  # 18 scalars read + 6 written per sample
-    # L2 rule: rotate over enough independent buffer sets that the data touched between two uses of the same set
-    # exceeds 3x the 126 MB L2, so no timed launch can be served from cache
-    nset = max(2, int(np.ceil(3 * 126e6 / alg_bytes)) + 1)
-    dev = torch.as_tensor(traj_host, device="cuda")
-    sets = []
-    for i in range(nset):
-        q, qd, qdd = (dev[:, k, :].t().contiguous() for k in range(3))
-        if i:  # distinct values per set (cheap perturbation), same distribution
-            q, qd, qdd = q + 1e-3 * i, qd * (1 + 1e-3 * i), qdd * (1 - 1e-3 * i)
-        sets.append((q, qd, qdd, torch.empty_like(q)))
-    del dev
-    step_no = [0]
-
-    def one_step():
-        q, qd, qdd, tau = sets[step_no[0] % nset]
-        step_no[0] += 1
-        model.rnea(q, qd, qdd, tau=tau)
+    wl = WORKLOADS[args.workload](args, model, rank, torch)
+    B = wl.B
 
     def barrier():
         if world > 1:
@@ -226,20 +337,20 @@ def run_gpu_arm(args):
 
     # ---- device-resident throughput -------------------------------------------------------------------
     for _ in range(args.warmup):
-        one_step()
+        wl.step()
     barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
-        # keep the sampler alive for >= ~0.3 s so it sees the loaded clocks: untimed extra launches first
+        # untimed launches first so that the sampler sees loaded clocks (>= ~0.3 s)
         t_end = time.perf_counter() + 0.3
         while time.perf_counter() < t_end:
-            one_step()
+            wl.step()
         barrier()
         e0.record()
         for a, b in evs:
             a.record()
-            one_step()
+            wl.step()
             b.record()
         e1.record()
         barrier()
@@ -251,15 +362,14 @@ def run_gpu_arm(args):
     total_ms, kern_ms_avg = t.tolist()
     value = world * B * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the host API (pinned host buffers, H2D + kernel + D2H inside the timed region) ----
-    tau_host = torch.empty((B, 6), dtype=tdt).pin_memory()
+    # ---- end to end through the public API (pinned host buffers; H2D + kernel + D2H inside the timed region) ----
     for _ in range(max(1, min(args.warmup, 3))):
-        model.rnea_host(traj_pinned, tau=tau_host)
+        wl.e2e_step()
     e2e_steps = max(1, min(args.steps, 20))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        model.rnea_host(traj_pinned, tau=tau_host)
+        wl.e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -269,33 +379,33 @@ def run_gpu_arm(args):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        achieved = alg_bytes / (kern_ms_avg * 1e-3) / 1e9
+        achieved = wl.alg_bytes / (kern_ms_avg * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(f"rnea_{args.dtype}_bytes_per_launch_at_{B}")
+                traffic = json.load(f).get(f"{args.workload}_{args.dtype}_{B}")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "layout": "SoA [3][6][B] resident in HBM", "kernel_path": model.kernel_path,
-                       "l2_policy": f"{nset} rotating buffer sets x {alg_bytes / 1e6:.0f} MB: >= {((nset - 1) * alg_bytes) / 1e6:.0f} MB touched between reuses (L2 = 126 MB)",
-                       "parallelism": f"samples sharded x{world}, no collective"},
+            "dtype": args.dtype if args.workload != "linearize" else "f64", "data": "synthetic",
+            "config": {"workload": wl.workload, "batch_per_gpu": B, "layout": wl.layout, "kernel_path": model.kernel_path,
+                       "l2_policy": f"{wl.nset} rotating buffer set(s) x {wl.alg_bytes / 1e6:.0f} MB algorithmic bytes per step (L2 = 126 MB)",
+                       "parallelism": f"samples sharded x{world}" + (", one 112-double NCCL all-reduce per step" if args.workload == "gram" and world > 1 else ", no collective")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel_ms": kern_ms_avg, "algorithmic_bytes_per_launch": alg_bytes},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 18 * esize * B, "d2h_bytes_per_step": 6 * esize * B,
-                    "api": "Model.rnea_host -> rbm_rnea_host_* (pinned host AoS in, pinned host out)", "steps": e2e_steps},
-            "gpu_launches": args.steps,
+                         "peak_source": peak_src, "kernel_ms": kern_ms_avg, "algorithmic_bytes_per_launch": wl.alg_bytes},
+            "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h, "api": wl.e2e_api, "steps": e2e_steps},
+            "gpu_launches": args.steps * wl.launches_per_step,
             "clocks": clk.summary(),
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.workload == "rnea":
             consts = consts_dict(c)
             cores = os.cpu_count() or 1
-            n_cpu = args.cpu_samples if args.cpu_samples > 0 else 1500 * cores
+            rate, _, _ = cpu_reference_rate(consts, cores * 100, cores)  # calibration
+            n_cpu = args.cpu_samples if args.cpu_samples > 0 else int(max(cores * 100, rate * 15.0))  # ~15 s of CPU work
             v, cores, wall = cpu_reference_rate(consts, n_cpu, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n_cpu} samples of the same distribution, per-sample oracle port of reference dynamics.inverse, {wall:.1f} s wall"}
+                                    "sample": f"{n_cpu} samples of the same distribution, per-sample oracle port of reference dynamics.inverse, {wall:.1f} s wall on {cores} processes"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -308,7 +418,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--samples", type=int, default=1 << 20, help="samples per GPU per step")
+    ap.add_argument("--workload", default="rnea", choices=["rnea", "gram", "linearize"], help="rnea = BASELINE.json configs[1] (the headline)")
+    ap.add_argument("--samples", type=int, default=1 << 20, help="samples (states) per GPU per step")
     ap.add_argument("--cpu-samples", type=int, default=0, help="CPU baseline sample count (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
