@@ -47,7 +47,8 @@ enum { RBM_MAX_JOINTS_ABI = 16 };
 
 /* rbm_model_create flags */
 enum {
-  RBM_FLAG_FORCE_GENERIC = 1 /* never select a structure-specialised kernel */
+  RBM_FLAG_FORCE_GENERIC = 1, /* never select a structure-specialised kernel */
+  RBM_FLAG_NO_TMA = 2         /* never use the bulk-async (TMA) pipelined kernel variants */
 };
 
 /* kernel path chosen for a model (rbm_model_kernel_path) */

@@ -210,6 +210,7 @@ int rbm_model_create(int nj, const double* hposes_Rt, const double* simats, cons
   if (!m) return invalid("rbm_model_create: out of host memory");
   m->nj = nj;
   m->device = device;
+  m->no_tma = (flags & RBM_FLAG_NO_TMA) != 0;
   m->gp64.assign(np, 0.0);
   double* g = m->gp64.data();
   static const double ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
@@ -377,7 +378,7 @@ int rbm_regressor_from_traj_f32(const rbm_model* m, const float* q, const float*
 
 size_t rbm_gram_workspace_bytes(const rbm_model* m, int64_t n) {
   if (!m) return 0;
-  return sizeof(double) * 70 * (size_t)gram_grid(m, n < 0 ? 0 : n);
+  return sizeof(double) * 70 * (size_t)gram_grid(m, n < 0 ? 0 : n, 2);  // upper bound over dtypes
 }
 int rbm_regressor_gram_f64(const rbm_model* m, const double* q, const double* qd, const double* qdd, const double* f, double* gram_pack,
                            void* workspace, size_t workspace_bytes, int64_t n, int64_t ld, void* stream) {

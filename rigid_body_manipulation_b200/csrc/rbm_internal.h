@@ -14,6 +14,7 @@ struct rbm_model {
   int nj = 0;
   int path = rbm::PATH_GENERIC;
   int device = 0;
+  bool no_tma = false;  // RBM_FLAG_NO_TMA: keep to the direct-load kernels (A/B comparisons, debugging)
   std::vector<double> gp64;  // generic packed parameters (rbm_model.cuh layout), host copies
   std::vector<float> gp32;
   double* d_gp64 = nullptr;  // device copies, staged into shared memory by every block
@@ -60,7 +61,7 @@ int launch_rnea_full(const rbm_model* m, const T* traj, T* tau, T* poses, T* twi
 
 
 // launchers (rbm_regressor.cu)
-int gram_grid(const rbm_model* m, int64_t n);
+int gram_grid(const rbm_model* m, int64_t n, int per_sm);
 template <class T>
 int launch_regressor_rows(const T* tw, const T* dtw, T* Y, int64_t n, cudaStream_t st);
 template <class T>

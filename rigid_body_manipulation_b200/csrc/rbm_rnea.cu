@@ -3,12 +3,43 @@
 // One sample per thread; consecutive threads own consecutive samples, so every SoA stream
 // (q_j, qd_j, qdd_j, tau_j) is read / written as fully coalesced 128-byte lines and nothing is
 // re-read: HBM traffic == algorithmic traffic == 24 * sizeof(T) bytes per sample.
+#include <cstdlib>
+
 #include "rbm_internal.h"
 #include "rbm_rnea.cuh"
 
 namespace rbm {
 
 constexpr int kBlock = 128;
+
+// griddepcontrol (sm_90+): no-ops when the kernel was not launched with the programmatic-serialisation attribute
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+static bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("RBM_NO_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
+// launch with programmatic stream serialisation allowed: the grid may start (and park in griddepcontrol.wait) while the
+// previous kernel of the stream is still draining, which removes the launch gap between back-to-back batches
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---------------------------------------------------------------------------------------------
 // fast path, SoA
@@ -17,6 +48,10 @@ template <class T, class D, bool OUT_TWIST>
 __global__ void __launch_bounds__(kBlock) k_rnea_fast_soa(const __grid_constant__ FastParams<T> P, const T* __restrict__ q,
                                                           const T* __restrict__ qd, const T* __restrict__ qdd, T* __restrict__ tau,
                                                           T* __restrict__ Vout, T* __restrict__ dVout, int64_t n, int64_t ld) {
+  // Programmatic dependent launch: let the next kernel in the stream be scheduled while this grid drains, and wait for
+  // the previous grid's memory to be visible before the first global read (stream-order semantics are unchanged).
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();
   const int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (s >= n) return;
   T rq[6], rqd[6], rqdd[6];
@@ -140,11 +175,11 @@ int launch_rnea_soa(const rbm_model* m, const T* q, const T* qd, const T* qdd, T
   const unsigned grid = grid_for(n);
   const bool tw = (V != nullptr);
   if (m->path == PATH_SEQ_ISO) {
-    if (tw) k_rnea_fast_soa<T, SeqIso, true><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld);
-    else k_rnea_fast_soa<T, SeqIso, false><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld);
+    if (tw) RBM_CUDA_TRY(launch_pdl(k_rnea_fast_soa<T, SeqIso, true>, grid, kBlock, 0, st, ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld));
+    else RBM_CUDA_TRY(launch_pdl(k_rnea_fast_soa<T, SeqIso, false>, grid, kBlock, 0, st, ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld));
   } else if (m->path == PATH_SEQ_RIGID) {
-    if (tw) k_rnea_fast_soa<T, SeqRigid, true><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld);
-    else k_rnea_fast_soa<T, SeqRigid, false><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld);
+    if (tw) RBM_CUDA_TRY(launch_pdl(k_rnea_fast_soa<T, SeqRigid, true>, grid, kBlock, 0, st, ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld));
+    else RBM_CUDA_TRY(launch_pdl(k_rnea_fast_soa<T, SeqRigid, false>, grid, kBlock, 0, st, ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld));
   } else {
     const int np = generic_param_count(m->nj);
     const size_t sm = sizeof(T) * np;

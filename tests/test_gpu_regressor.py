@@ -42,6 +42,23 @@ def test_fused_regressor_from_trajectory(fname, force_generic):
     assert rel_err(o32["Y"].cpu().numpy(), g["regressor"]).max() < 1e-4
 
 
+@pytest.mark.parametrize("n", [4096, 262_144 + 256 * 5 + 100])
+def test_gram_fp32_mode(n):
+    g = load_golden("ref_inverse_hammer.npz")
+    rng = np.random.default_rng(n)
+    traj = sample_states(rng, n)
+    f = rng.standard_normal((n, 6)) * np.array([5, 5, 5, 1, 1, 1.0])
+    _, ref = _gram_reference(g, traj, f)
+    q, qd, qdd = soa(traj, torch.float32)
+    fd = torch.as_tensor(f, dtype=torch.float32, device="cuda").t().contiguous()
+    for no_tma in (False, True):
+        m = model_from_golden(g, no_tma=no_tma)
+        pack = m.regressor_gram(q, qd, qdd, fd).cpu().numpy()
+        assert np.abs(pack[:100] - ref[:100]).max() < 1e-4 * np.abs(ref[:100]).max()
+        assert np.abs(pack[100:110] - ref[100:110]).max() < 1e-4 * np.abs(ref[:100]).max()
+        assert pack[111] == n
+
+
 def _gram_reference(g, traj, f):
     nj = g["uscrews"].shape[0]
     kw = dict(wrench_tip=g["wrench_tip"], pose_tip_Rt=g["pose_tip"]) if "wrench_tip" in g.files else {}
@@ -52,10 +69,13 @@ def _gram_reference(g, traj, f):
 
 
 @pytest.mark.parametrize("fname", ["ref_inverse_hammer.npz", "ref_inverse_generic_nj6.npz", "ref_inverse_generic_nj9.npz"])
-@pytest.mark.parametrize("n", [1, 255, 4096, 100_003])
-def test_gram_matches_materialised_normal_equations(fname, n):
+@pytest.mark.parametrize("n", [1, 255, 4096, 100_003, 100_352, 300_002])
+@pytest.mark.parametrize("no_tma", [False, True])
+def test_gram_matches_materialised_normal_equations(fname, n, no_tma):
+    """n = 4096 / 100_352 / 300_002 take the TMA-pipelined kernel on the fast path (the last with a ragged 226-sample tail);
+    odd n (row pitch not 16-byte aligned in fp64), n < 256, generic models and no_tma=True take the direct-load kernel."""
     g = load_golden(fname)
-    m = model_from_golden(g)
+    m = model_from_golden(g, no_tma=no_tma)
     nj = m.nj
     rng = np.random.default_rng(n)
     traj = sample_states(rng, n) if nj == 6 else np.stack([rng.uniform(-3, 3, (n, nj)), rng.standard_normal((n, nj)), rng.standard_normal((n, nj))], 1)
