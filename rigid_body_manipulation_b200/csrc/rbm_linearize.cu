@@ -23,6 +23,9 @@
 namespace rbm {
 
 constexpr int kLinBlock = 128;
+#ifndef RBM_LIN_MINB
+#define RBM_LIN_MINB 3
+#endif
 
 // ---- inverse-dynamics evaluators ---------------------------------------------------------------------
 template <class T, class D>
@@ -39,11 +42,17 @@ struct FastEval {
     return r;
   }
   __device__ __forceinline__ void trig(const T (&q)[6], T (&c)[6], T (&s)[6]) const { fast_sincos<T, D>(q, c, s); }
-  __device__ __forceinline__ void id(const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6], const T (&qdd)[6], bool gravity,
-                                     T (&tau)[6]) const {
-    const T g[3] = {gravity ? P.g[0] : T(0), gravity ? P.g[1] : T(0), gravity ? P.g[2] : T(0)};
+  __device__ __forceinline__ static bool q_matters(int j) { return D::q_matters(j); }
+  __device__ __forceinline__ void id(const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6], const T (&qdd)[6], T (&tau)[6]) const {
     FastResult<T> r;
-    fast_rnea_core<T, D, true>(P, g, q, c, s, qd, qdd, r);
+    fast_rnea_core<T, D, true>(P, P.g, q, c, s, qd, qdd, r);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tau[k] = r.tau[k];
+  }
+  // acceleration-only evaluation without gravity: column of the joint-space inertia matrix for qdd = e_j
+  __device__ __forceinline__ void id_inertia(const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qdd)[6], T (&tau)[6]) const {
+    FastResult<T> r;
+    fast_rnea_core<T, D, true, false, false>(P, P.g, q, c, s, qdd /* unused */, qdd, r);
 #pragma unroll
     for (int k = 0; k < 6; ++k) tau[k] = r.tau[k];
   }
@@ -59,9 +68,16 @@ struct GenericEval {
   __device__ __forceinline__ int nj() const { return nj_; }
   __device__ __forceinline__ static bool is_hinge(int) { return false; }  // generic_rnea evaluates its own trigonometry
   __device__ __forceinline__ void trig(const T (&)[MAXJ], T (&)[MAXJ], T (&)[MAXJ]) const {}
-  __device__ __forceinline__ void id(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qd)[MAXJ], const T (&qdd)[MAXJ], bool gravity,
+  __device__ __forceinline__ static bool q_matters(int) { return true; }
+  __device__ __forceinline__ void id(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qd)[MAXJ], const T (&qdd)[MAXJ],
                                      T (&tau)[MAXJ]) const {
-    generic_rnea<T, 0>(sp, gravity ? sp : zero, nj_, q, qd, qdd, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
+    generic_rnea<T, 0>(sp, sp, nj_, q, qd, qdd, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
+  }
+  __device__ __forceinline__ void id_inertia(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qdd)[MAXJ], T (&tau)[MAXJ]) const {
+    T qd0[MAXJ];
+#pragma unroll
+    for (int k = 0; k < MAXJ; ++k) qd0[k] = T(0);
+    generic_rnea<T, 0>(sp, zero, nj_, q, qd0, qdd, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
   }
 };
 
@@ -139,7 +155,7 @@ __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict
     T e[MJ], col[MJ];
 #pragma unroll
     for (int k = 0; k < MJ; ++k) e[k] = (k == j) ? T(1) : T(0);
-    ev.id(q, c, sn, zero, e, false, col);
+    ev.id_inertia(q, c, sn, e, col);
 #pragma unroll
     for (int r = 0; r < MJ; ++r)
 #pragma unroll
@@ -148,7 +164,7 @@ __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict
   }
   // bias forces and nominal acceleration
   T h[MJ], qdd[MJ];
-  ev.id(q, c, sn, qd, zero, true, h);
+  ev.id(q, c, sn, qd, zero, h);
   cholesky<T, MJ>(M, nj);
 #pragma unroll
   for (int k = 0; k < MJ; ++k) qdd[k] = u[k] - h[k];
@@ -175,7 +191,7 @@ __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict
   }
   // reference value for forward differences: ID at the nominal point (== u up to round-off)
   T tau0[MJ];
-  if (!centered) ev.id(q, c, sn, qd, qdd, true, tau0);
+  if (!centered) ev.id(q, c, sn, qd, qdd, tau0);
   const T inv_step = centered ? T(1) / (T(2) * eps) : T(1) / eps;
 
   // position columns, then velocity columns
@@ -185,6 +201,17 @@ __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict
     for (int j = 0; j < nj; ++j) {
       T xp[MJ], cp[MJ], sp_[MJ], tp[MJ], tm[MJ];
       const T* src = pass == 0 ? q : qd;
+      const int col = pass * nj + j;
+      if (pass == 0 && !E::q_matters(j)) {  // d tau / d q_j is structurally zero: the column is that of the identity map
+#pragma unroll
+        for (int r = 0; r < MJ; ++r) {
+          if (r < nj) {
+            A[((int64_t)r * ns + col) * ld + s] = (r == j) ? T(1) : T(0);
+            A[((int64_t)(nj + r) * ns + col) * ld + s] = T(0);
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int k = 0; k < MJ; ++k) { xp[k] = src[k] + ((k == j) ? eps : T(0)); cp[k] = c[k]; sp_[k] = sn[k]; }
       if (pass == 0 && E::is_hinge(j)) {
@@ -195,8 +222,8 @@ __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict
 #pragma unroll
         for (int k = 0; k < MJ; ++k) { cp[k] = (k == j) ? cj : cp[k]; sp_[k] = (k == j) ? sj : sp_[k]; }
       }
-      if (pass == 0) ev.id(xp, cp, sp_, qd, qdd, true, tp);
-      else ev.id(q, c, sn, xp, qdd, true, tp);
+      if (pass == 0) ev.id(xp, cp, sp_, qd, qdd, tp);
+      else ev.id(q, c, sn, xp, qdd, tp);
       if (centered) {
 #pragma unroll
         for (int k = 0; k < MJ; ++k) { xp[k] = src[k] - ((k == j) ? eps : T(0)); cp[k] = c[k]; sp_[k] = sn[k]; }
@@ -208,8 +235,8 @@ __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict
 #pragma unroll
           for (int k = 0; k < MJ; ++k) { cp[k] = (k == j) ? cj : cp[k]; sp_[k] = (k == j) ? sj : sp_[k]; }
         }
-        if (pass == 0) ev.id(xp, cp, sp_, qd, qdd, true, tm);
-        else ev.id(q, c, sn, xp, qdd, true, tm);
+        if (pass == 0) ev.id(xp, cp, sp_, qd, qdd, tm);
+        else ev.id(q, c, sn, xp, qdd, tm);
       } else {
 #pragma unroll
         for (int k = 0; k < MJ; ++k) tm[k] = tau0[k];
@@ -218,7 +245,6 @@ __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict
 #pragma unroll
       for (int k = 0; k < MJ; ++k) x[k] = -(tp[k] - tm[k]) * inv_step;
       chol_solve<T, MJ>(M, nj, x);   // column j of Q (pass 0) or V (pass 1)
-      const int col = pass * nj + j;
 #pragma unroll
       for (int r = 0; r < MJ; ++r) {
         if (r < nj) {
@@ -235,7 +261,7 @@ __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict
 }
 
 template <class T, class D>
-__global__ void __launch_bounds__(kLinBlock) k_linearize_fast(const __grid_constant__ FastParams<T> P, const T* __restrict__ q, const T* __restrict__ qd,
+__global__ void __launch_bounds__(kLinBlock, RBM_LIN_MINB) k_linearize_fast(const __grid_constant__ FastParams<T> P, const T* __restrict__ q, const T* __restrict__ qd,
                                                               const T* __restrict__ u, T dt, T eps, int centered, T* __restrict__ A, T* __restrict__ B,
                                                               T* __restrict__ qdd_out, int64_t n, int64_t ld) {
   const int64_t s = (int64_t)blockIdx.x * kLinBlock + threadIdx.x;

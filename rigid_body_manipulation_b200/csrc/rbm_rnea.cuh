@@ -36,6 +36,12 @@ struct SequentialDesc {
   using L3 = LinkD<JOINT_RZ, SPerm<1, 3, -2>, false, IK15>;
   using L4 = LinkD<JOINT_RZ, SPerm<-3, 2, 1>, false, IK15>;
   using L5 = LinkD<JOINT_RZ, SPerm<1, -3, 2>, false, INERTIA_RIGID>;
+  // Does tau depend on q_j at all?  For the three leading prismatic joints it does not: a joint translation enters only
+  // through p_j x (.) terms -- forward with the parent's angular velocity / acceleration (structurally zero: every earlier
+  // joint is prismatic too) and backward in the MOMENT transported to links 0..2, which no prismatic joint force reads.
+  // (The same dead-code argument is what lets nvcc drop those terms from the kernel.)  Used by the linearisation to skip
+  // finite differences that are identically zero; verified against the oracle in tests/test_gpu_linearize.py.
+  static constexpr bool q_matters(int j) { return j >= 3; }
 };
 using SeqIso = SequentialDesc<INERTIA_ISO>;
 using SeqRigid = SequentialDesc<INERTIA_RIGID>;
@@ -93,8 +99,8 @@ RBM_HD auto fwd_wrench(const FastParams<T>& P, const VV& v, const WW& w, const A
 }
 
 // One forward step (Eq. 8.50-8.52) plus the link's body wrench.
-template <class L, int I, class T, class VV, class WW, class AA, class LL>
-RBM_HD auto fwd_link(const FastParams<T>& P, T q, T qd, T qdd, T c, T s, const VV& vp, const WW& wp, const AA& ap, const LL& lp) {
+template <class L, int I, class T, class QD, class VV, class WW, class AA, class LL>
+RBM_HD auto fwd_link(const FastParams<T>& P, T q, QD qd, T qdd, T c, T s, const VV& vp, const WW& wp, const AA& ap, const LL& lp) {
   // translation of T_i = exp(-S q) * M_i
   auto tm = [&] {
     if constexpr (L::has_t) return ld3(P.tm[I]);
@@ -159,7 +165,7 @@ RBM_HD void fast_sincos(const T (&q)[6], T (&c)[6], T (&s)[6]) {
   if constexpr (D::L5::jk == JOINT_RZ) sincos_t(q[5], &s[5], &c[5]);
 }
 
-template <class T, class D, bool WANT_TAU>
+template <class T, class D, bool WANT_TAU, bool VEL = true, bool GRAV = true>
 RBM_HD void fast_rnea_core(const FastParams<T>& P, const T* g, const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6],
                            const T (&qdd)[6], FastResult<T>& out);
 
@@ -180,20 +186,29 @@ RBM_HD void fast_rnea(const FastParams<T>& P, const T (&q)[6], const T (&qd)[6],
 
 // The recursion itself; `g` is the linear part of the base acceleration (P.g, or zeros when the joint-space inertia
 // matrix is being extracted column by column).
-template <class T, class D, bool WANT_TAU>
+// VEL = false treats every joint velocity as a structural zero and GRAV = false the base acceleration (together: the
+// acceleration-only evaluation ID(q, 0, qdd) without gravity whose columns are the joint-space inertia matrix).
+template <class T, class D, bool WANT_TAU, bool VEL, bool GRAV>
 RBM_HD void fast_rnea_core(const FastParams<T>& P, const T* g, const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6],
                            const T (&qdd)[6], FastResult<T>& out) {
   // base: twist_0 = 0, dtwist_0 = [g; 0]  (core/simulate.py:149,154-155)
   auto v0 = Z3{};
   auto w0 = Z3{};
-  auto a0 = ld3(g);
+  auto a0 = [&] {
+    if constexpr (GRAV) return ld3(g);
+    else return Z3{};
+  }();
   auto l0 = Z3{};
-  auto k0 = fwd_link<typename D::L0, 0>(P, q[0], qd[0], qdd[0], c[0], s[0], v0, w0, a0, l0);
-  auto k1 = fwd_link<typename D::L1, 1>(P, q[1], qd[1], qdd[1], c[1], s[1], k0.v, k0.w, k0.a, k0.l);
-  auto k2 = fwd_link<typename D::L2, 2>(P, q[2], qd[2], qdd[2], c[2], s[2], k1.v, k1.w, k1.a, k1.l);
-  auto k3 = fwd_link<typename D::L3, 3>(P, q[3], qd[3], qdd[3], c[3], s[3], k2.v, k2.w, k2.a, k2.l);
-  auto k4 = fwd_link<typename D::L4, 4>(P, q[4], qd[4], qdd[4], c[4], s[4], k3.v, k3.w, k3.a, k3.l);
-  auto k5 = fwd_link<typename D::L5, 5>(P, q[5], qd[5], qdd[5], c[5], s[5], k4.v, k4.w, k4.a, k4.l);
+  auto vel = [&](int i) {
+    if constexpr (VEL) return qd[i];
+    else return Z{};
+  };
+  auto k0 = fwd_link<typename D::L0, 0>(P, q[0], vel(0), qdd[0], c[0], s[0], v0, w0, a0, l0);
+  auto k1 = fwd_link<typename D::L1, 1>(P, q[1], vel(1), qdd[1], c[1], s[1], k0.v, k0.w, k0.a, k0.l);
+  auto k2 = fwd_link<typename D::L2, 2>(P, q[2], vel(2), qdd[2], c[2], s[2], k1.v, k1.w, k1.a, k1.l);
+  auto k3 = fwd_link<typename D::L3, 3>(P, q[3], vel(3), qdd[3], c[3], s[3], k2.v, k2.w, k2.a, k2.l);
+  auto k4 = fwd_link<typename D::L4, 4>(P, q[4], vel(4), qdd[4], c[4], s[4], k3.v, k3.w, k3.a, k3.l);
+  auto k5 = fwd_link<typename D::L5, 5>(P, q[5], vel(5), qdd[5], c[5], s[5], k4.v, k4.w, k4.a, k4.l);
 
   out.v[0] = to_scalar<T>(k5.v.x); out.v[1] = to_scalar<T>(k5.v.y); out.v[2] = to_scalar<T>(k5.v.z);
   out.w[0] = to_scalar<T>(k5.w.x); out.w[1] = to_scalar<T>(k5.w.y); out.w[2] = to_scalar<T>(k5.w.z);

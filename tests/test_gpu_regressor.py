@@ -72,8 +72,8 @@ def _gram_reference(g, traj, f):
 @pytest.mark.parametrize("n", [1, 255, 4096, 100_003, 100_352, 300_002])
 @pytest.mark.parametrize("no_tma", [False, True])
 def test_gram_matches_materialised_normal_equations(fname, n, no_tma):
-    """n = 4096 / 100_352 / 300_002 take the TMA-pipelined kernel on the fast path (the last with a ragged 226-sample tail);
-    odd n (row pitch not 16-byte aligned in fp64), n < 256, generic models and no_tma=True take the direct-load kernel."""
+    """fp64 always takes the direct-load kernel (the TMA-pipelined variant is used in fp32 mode only, see
+    test_gram_fp32_mode); sizes cover single-CTA, multi-wave and ragged-tail cases for fast and generic models."""
     g = load_golden(fname)
     m = model_from_golden(g, no_tma=no_tma)
     nj = m.nj
