@@ -201,7 +201,7 @@ class RneaWorkload:
         self.traj_pinned = torch.as_tensor(host).pin_memory()
         # L2 rule: rotate over enough independent buffer sets that the data touched between two uses of one set
         # exceeds 3x the 126 MB L2, so no timed launch can be served from cache
-        self.nset = max(2, int(np.ceil(3 * L2_BYTES / self.alg_bytes)) + 1)
+        self.nset = 1 if self.alg_bytes > 16 * L2_BYTES else max(2, int(np.ceil(3 * L2_BYTES / self.alg_bytes)) + 1)
         dev = torch.as_tensor(host, device="cuda")
         self.sets = []
         for i in range(self.nset):

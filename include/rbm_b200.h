@@ -101,6 +101,16 @@ RBM_API int rbm_rnea_aos_f32(const rbm_model* m, const float* traj, float* tau, 
 RBM_API int rbm_rnea_full_f64(const rbm_model* m, const double* traj, double* tau, double* poses, double* twists, double* dtwists,
                       int64_t n, void* stream);
 
+/* Planner-driven inverse dynamics: the quintic rest-to-rest trajectory of planners/joint_position_planner.py:86-131
+ * (traj_5th_spline) is evaluated inside the kernel, so nothing is read from HBM.  Sample s is step k = step0 + s*stride:
+ *   prof = coeffs . [k^5 .. 1];  q_j = disp_j prof + offset_j;  qd_j = disp_j prof' / timestep;  qdd_j = disp_j prof'' / timestep^2
+ * coeffs [6], disp [nj], offset [nj] are HOST pointers (the six coefficients come from the planner's own 6x6 solve).
+ *   tau : [nj][ld];   traj : [3*nj][ld] (rows q_0..q_nj-1, qd_*, qdd_*) or NULL. */
+RBM_API int rbm_rnea_planned_f64(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double timestep, double step0,
+                         double stride, double* tau, double* traj, int64_t n, int64_t ld, void* stream);
+RBM_API int rbm_rnea_planned_f32(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double timestep, double step0,
+                         double stride, float* tau, float* traj, int64_t n, int64_t ld, void* stream);
+
 /* End-to-end convenience for host callers (the `e2e` measurement): traj_host [n][3][nj] and tau_host [n][nj] are HOST
  * buffers (pinned memory gives full PCIe rate); copies host->device, runs the AoS kernel and copies back in
  * `chunk`-sample pieces on internal streams so transfers overlap compute.  Synchronous: returns when tau_host is

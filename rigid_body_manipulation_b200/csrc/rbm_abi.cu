@@ -305,6 +305,24 @@ int rbm_rnea_aos_f32(const rbm_model* m, const float* traj, float* tau, int64_t 
   return launch_rnea_aos<float>(m, traj, tau, n, (cudaStream_t)stream);
 }
 
+int rbm_rnea_planned_f64(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double timestep, double step0, double stride,
+                         double* tau, double* traj, int64_t n, int64_t ld, void* stream) {
+  RBM_CHECK_BATCH("rbm_rnea_planned_f64")
+  if (!coeffs || !disp || !offset || !tau) return invalid("rbm_rnea_planned_f64: NULL pointer");
+  if (ld < n) return invalid("rbm_rnea_planned_f64: ld < n");
+  if (!(timestep > 0.0)) return invalid("rbm_rnea_planned_f64: timestep must be positive");
+  return launch_rnea_planned<double>(m, coeffs, disp, offset, timestep, step0, stride, tau, traj, n, ld, (cudaStream_t)stream);
+}
+
+int rbm_rnea_planned_f32(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double timestep, double step0, double stride,
+                         float* tau, float* traj, int64_t n, int64_t ld, void* stream) {
+  RBM_CHECK_BATCH("rbm_rnea_planned_f32")
+  if (!coeffs || !disp || !offset || !tau) return invalid("rbm_rnea_planned_f32: NULL pointer");
+  if (ld < n) return invalid("rbm_rnea_planned_f32: ld < n");
+  if (!(timestep > 0.0)) return invalid("rbm_rnea_planned_f32: timestep must be positive");
+  return launch_rnea_planned<float>(m, coeffs, disp, offset, timestep, step0, stride, tau, traj, n, ld, (cudaStream_t)stream);
+}
+
 int rbm_rnea_full_f64(const rbm_model* m, const double* traj, double* tau, double* poses, double* twists, double* dtwists, int64_t n,
                       void* stream) {
   RBM_CHECK_BATCH("rbm_rnea_full_f64")

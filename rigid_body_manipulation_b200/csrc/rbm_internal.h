@@ -57,6 +57,9 @@ int launch_rnea_soa(const rbm_model* m, const T* q, const T* qd, const T* qdd, T
 template <class T>
 int launch_rnea_aos(const rbm_model* m, const T* traj, T* tau, int64_t n, cudaStream_t st);
 template <class T>
+int launch_rnea_planned(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double timestep, double step0, double stride,
+                        T* tau, T* traj, int64_t n, int64_t ld, cudaStream_t st);
+template <class T>
 int launch_rnea_full(const rbm_model* m, const T* traj, T* tau, T* poses, T* twists, T* dtwists, int64_t n, cudaStream_t st);
 
 

@@ -165,6 +165,86 @@ __global__ void __launch_bounds__(kBlock) k_rnea_generic_aos(const T* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// planner-driven kernels: the quintic rest-to-rest trajectory (reference planners/joint_position_planner.py:86-131)
+// is evaluated in the kernel from its six coefficients, so a planned batch reads nothing from HBM and writes tau only.
+// ---------------------------------------------------------------------------------------------
+// The profile is always evaluated in double, also in fp32 mode: in the power basis of the integer step variable
+// (k^5 up to ~1e16 against coefficients down to ~1e-16) single precision would lose every digit to cancellation.
+template <class T>
+struct PlanArg {
+  double coeffs[6];          // s(k) = c0 k^5 + c1 k^4 + ... + c5   (normalised profile in the step variable k)
+  double inv_dt, inv_dt2;    // 1 / timestep, 1 / timestep^2
+  double step0, stride;      // sample s evaluates step k = step0 + s * stride
+  T disp[RBM_MAX_JOINTS];    // displacement per joint
+  T offset[RBM_MAX_JOINTS];  // pos_offset per joint
+};
+
+template <class T>
+__device__ __forceinline__ void plan_profile(const PlanArg<T>& pl, int64_t s, T& sp, T& sv, T& sa) {
+  const double k = pl.step0 + (double)s * pl.stride;
+  const double k2 = k * k, k3 = k2 * k, k4 = k3 * k, k5 = k4 * k;
+  const double* c = pl.coeffs;
+  sp = (T)(c[0] * k5 + c[1] * k4 + c[2] * k3 + c[3] * k2 + c[4] * k + c[5]);                                  // :120,125
+  sv = (T)((5.0 * c[0] * k4 + 4.0 * c[1] * k3 + 3.0 * c[2] * k2 + 2.0 * c[3] * k + c[4]) * pl.inv_dt);        // :121,126
+  sa = (T)((20.0 * c[0] * k3 + 12.0 * c[1] * k2 + 6.0 * c[2] * k + 2.0 * c[3]) * pl.inv_dt2);                 // :122-123,127
+}
+
+template <class T, class D>
+__global__ void __launch_bounds__(kBlock) k_rnea_planned_fast(const __grid_constant__ FastParams<T> P, const __grid_constant__ PlanArg<T> pl,
+                                                              T* __restrict__ tau, T* __restrict__ traj /* [3*6][ld] or null */, int64_t n, int64_t ld) {
+  const int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (s >= n) return;
+  T sp, sv, sa;
+  plan_profile(pl, s, sp, sv, sa);
+  T rq[6], rqd[6], rqdd[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    rq[j] = pl.disp[j] * sp + pl.offset[j];
+    rqd[j] = pl.disp[j] * sv;
+    rqdd[j] = pl.disp[j] * sa;
+  }
+  FastResult<T> r;
+  fast_rnea<T, D, true>(P, rq, rqd, rqdd, r);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) tau[j * ld + s] = r.tau[j];
+  if (traj) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      traj[j * ld + s] = rq[j];
+      traj[(6 + j) * ld + s] = rqd[j];
+      traj[(12 + j) * ld + s] = rqdd[j];
+    }
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_rnea_planned_generic(const T* __restrict__ gp, int nj, int nparams, const __grid_constant__ PlanArg<T> pl,
+                                                                 T* __restrict__ tau, T* __restrict__ traj, int64_t n, int64_t ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sp_ = reinterpret_cast<T*>(smem_raw);
+  stage_params(gp, nparams, sp_);
+  const int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (s >= n) return;
+  T sp, sv, sa;
+  plan_profile(pl, s, sp, sv, sa);
+  T rq[RBM_MAX_JOINTS], rqd[RBM_MAX_JOINTS], rqdd[RBM_MAX_JOINTS], rtau[RBM_MAX_JOINTS];
+  for (int j = 0; j < nj; ++j) {
+    rq[j] = pl.disp[j] * sp + pl.offset[j];
+    rqd[j] = pl.disp[j] * sv;
+    rqdd[j] = pl.disp[j] * sa;
+  }
+  generic_rnea<T, 0>(sp_, sp_, nj, rq, rqd, rqdd, rtau, nullptr, nullptr, nullptr, nullptr, nullptr);
+  for (int j = 0; j < nj; ++j) {
+    tau[j * ld + s] = rtau[j];
+    if (traj) {
+      traj[j * ld + s] = rq[j];
+      traj[(nj + j) * ld + s] = rqd[j];
+      traj[(2 * nj + j) * ld + s] = rqdd[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
@@ -215,6 +295,37 @@ int launch_rnea_full(const rbm_model* m, const T* traj, T* tau, T* poses, T* twi
   return RBM_OK;
 }
 
+template <class T>
+int launch_rnea_planned(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double timestep, double step0, double stride,
+                        T* tau, T* traj, int64_t n, int64_t ld, cudaStream_t st) {
+  if (n == 0) return RBM_OK;
+  PlanArg<T> pl;
+  for (int k = 0; k < 6; ++k) pl.coeffs[k] = coeffs[k];
+  for (int k = 0; k < RBM_MAX_JOINTS; ++k) {
+    pl.disp[k] = k < m->nj ? (T)disp[k] : T(0);
+    pl.offset[k] = k < m->nj ? (T)offset[k] : T(0);
+  }
+  pl.inv_dt = 1.0 / timestep;
+  pl.inv_dt2 = 1.0 / (timestep * timestep);
+  pl.step0 = step0;
+  pl.stride = stride;
+  const unsigned grid = grid_for(n);
+  if (m->path == PATH_SEQ_ISO) {
+    k_rnea_planned_fast<T, SeqIso><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), pl, tau, traj, n, ld);
+  } else if (m->path == PATH_SEQ_RIGID) {
+    k_rnea_planned_fast<T, SeqRigid><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), pl, tau, traj, n, ld);
+  } else {
+    const int np = generic_param_count(m->nj);
+    k_rnea_planned_generic<T><<<grid, kBlock, sizeof(T) * np, st>>>(ModelView<T>::generic(m), m->nj, np, pl, tau, traj, n, ld);
+  }
+  RBM_CUDA_TRY(cudaGetLastError());
+  return RBM_OK;
+}
+
+template int launch_rnea_planned<double>(const rbm_model*, const double*, const double*, const double*, double, double, double, double*, double*, int64_t,
+                                         int64_t, cudaStream_t);
+template int launch_rnea_planned<float>(const rbm_model*, const double*, const double*, const double*, double, double, double, float*, float*, int64_t,
+                                        int64_t, cudaStream_t);
 template int launch_rnea_soa<double>(const rbm_model*, const double*, const double*, const double*, double*, double*, double*, int64_t, int64_t, cudaStream_t);
 template int launch_rnea_soa<float>(const rbm_model*, const float*, const float*, const float*, float*, float*, float*, int64_t, int64_t, cudaStream_t);
 template int launch_rnea_aos<double>(const rbm_model*, const double*, double*, int64_t, cudaStream_t);

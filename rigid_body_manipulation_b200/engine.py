@@ -160,6 +160,29 @@ class Model:
         _lib.check(rc, "rbm_rnea_full")
         return tau, poses, tw, dtw
 
+    # ---- planner-driven: trajectory generated in the kernel (no input traffic) -------------------------------------
+    def rnea_planned(self, plan, n=None, step0=None, stride=1.0, dtype=torch.float64, want_traj=False, tau=None):
+        """tau (nj, n) for steps step0 + s*stride of a planner.QuinticPlan (defaults: every planned step).
+        With want_traj also returns the generated (q, qd, qdd) as a (3, nj, n) tensor."""
+        n = plan.n_steps if n is None else int(n)
+        step0 = float(plan.init_step if step0 is None else step0)
+        if len(plan.displacement) != self.nj or len(plan.pos_offset) != self.nj:
+            raise ValueError(f"plan must have {self.nj} joints")
+        if dtype not in (torch.float64, torch.float32):
+            raise ValueError("dtype must be float64 or float32")
+        if tau is None:
+            tau = torch.empty((self.nj, n), dtype=dtype, device=self.device)
+        self._check_dev(tau)
+        traj = torch.empty((3, self.nj, n), dtype=dtype, device=self.device) if want_traj else None
+        co = np.ascontiguousarray(plan.coeffs, dtype=np.float64)
+        di = np.ascontiguousarray(plan.displacement, dtype=np.float64)
+        of = np.ascontiguousarray(plan.pos_offset, dtype=np.float64)
+        fn = self._lib.rbm_rnea_planned_f64 if dtype == torch.float64 else self._lib.rbm_rnea_planned_f32
+        with torch.cuda.device(self.device):
+            rc = fn(self._h, _ptr(co), _ptr(di), _ptr(of), float(plan.timestep), step0, float(stride), _ptr(tau), _ptr(traj), n, n, self._stream())
+        _lib.check(rc, "rbm_rnea_planned")
+        return (tau, traj) if want_traj else tau
+
     # ---- host end-to-end ---------------------------------------------------------------------------
     def rnea_host(self, traj, tau=None, chunk=0):
         """traj: HOST array / pinned CPU tensor (n, 3, nj); returns tau on the host (same kind).  H2D, kernel and D2H are

@@ -157,3 +157,25 @@ def test_invalid_arguments_raise():
     bad[3, 2, 2] = np.nan
     with pytest.raises(ValueError):
         Model(g["hposes_Rt"], bad, g["uscrews"], g["twist_0"], g["dtwist_0"])
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_planned_trajectory_kernel_matches_config1(force_generic):
+    """the quintic planner evaluated in-kernel (no input traffic) reproduces the reference's planned
+    trajectory (planners/joint_position_planner.py:86-131) and its feed-forward tau for all 1500 steps of base.yaml."""
+    from rigid_body_manipulation_b200.planner import traj_5th_spline
+
+    g = load_golden("ref_inverse_hammer.npz")
+    c1 = load_golden("ref_config1_hammer.npz")
+    pg = load_golden("ref_planner.npz")
+    m = model_from_golden(g, force_generic=force_generic)
+    plan = traj_5th_spline(pg["base_disp"], [1, 1, 1, 0, 0, 0], 0.002, int(pg["base_n_steps"]))
+    tau, traj = m.rnea_planned(plan, want_traj=True)
+    traj = traj.permute(2, 0, 1).cpu().numpy()  # (n, 3, 6)
+    assert np.abs(traj - c1["traj"]).max() < 1e-11 * np.abs(c1["traj"]).max()
+    assert rel_err(tau.t().cpu().numpy(), c1["tau"]).max() < TOL64
+    # sub-sampled (every 10th step = the 50 fps frame grid of core/simulate.py:196) and fp32
+    tau10 = m.rnea_planned(plan, n=150, step0=0, stride=10.0)
+    assert rel_err(tau10.t().cpu().numpy(), c1["tau"][::10]).max() < TOL64
+    tau32 = m.rnea_planned(plan, dtype=torch.float32)
+    assert rel_err(tau32.t().cpu().numpy(), c1["tau"]).max() < TOL32  # the profile itself is evaluated in double in both modes
