@@ -152,6 +152,18 @@ RBM_API int rbm_regressor_gram_f64(const rbm_model* m, const double* q, const do
 RBM_API int rbm_regressor_gram_f32(const rbm_model* m, const float* q, const float* qd, const float* qdd, const float* f, double* gram_pack,
                            void* workspace, size_t workspace_bytes, int64_t n, int64_t ld, void* stream);
 
+/* ---- the one collective: all-reduce of the Gram pack over NCCL ------------------------------------------------
+ * Each rank accumulates the pack of its shard (rbm_regressor_gram_*), then rbm_allreduce_gram sums the 112 doubles in place
+ * across ranks on `stream` (enqueue it right behind the Gram call: no host synchronisation is needed in between).
+ * NCCL is resolved with dlopen at first use (libnccl.so.2); rbm_nccl_available() == 0 when it cannot be found.
+ * Communicator set-up: rank 0 calls rbm_nccl_unique_id (128 bytes), the application broadcasts those bytes, every rank calls
+ * rbm_nccl_comm_create (collective).  `comm` is an opaque ncclComm_t. */
+RBM_API int rbm_nccl_available(void);
+RBM_API int rbm_nccl_unique_id(void* id128);
+RBM_API int rbm_nccl_comm_create(const void* id128, int nranks, int rank, int device, void** comm);
+RBM_API int rbm_nccl_comm_destroy(void* comm);
+RBM_API int rbm_allreduce_gram(void* comm, double* gram_pack, void* stream);
+
 /* ---- LQR linearisation ------------------------------------------------------------------------------------
  * Replaces dynamics.StateSpace.update_matrices (dynamics/dynamics.py:41-46 -> mjd_transitionFD, consumed by
  * controllers/lqr.py:43-49) for the reference's plant (nv = nu = nj, unit-gear motors, semi-implicit Euler with

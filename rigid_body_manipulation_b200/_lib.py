@@ -29,6 +29,10 @@ class RbmCudaError(RbmError):
     pass
 
 
+class RbmNcclError(RbmError):
+    pass
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -61,6 +65,11 @@ SIGNATURES = {
     "rbm_gram_workspace_bytes": (C.c_size_t, [_vp, _i64]),
     "rbm_regressor_gram_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i64, _i64, _vp]),
     "rbm_regressor_gram_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _i64, _i64, _vp]),
+    "rbm_nccl_available": (C.c_int, []),
+    "rbm_nccl_unique_id": (C.c_int, [_vp]),
+    "rbm_nccl_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "rbm_nccl_comm_destroy": (C.c_int, [_vp]),
+    "rbm_allreduce_gram": (C.c_int, [_vp, _vp, _vp]),
     "rbm_linearize_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp, _i64, _i64, _vp]),
     "rbm_transfer_simat_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rbm_coordinate_transfer_simat_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
@@ -114,4 +123,6 @@ def check(rc: int, what: str = ""):
         raise RbmCudaError(msg)
     if rc == RBM_ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
+    if rc == RBM_ERR_NCCL:
+        raise RbmNcclError(msg)
     raise RbmError(f"{msg} (status {rc})")

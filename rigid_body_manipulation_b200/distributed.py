@@ -31,6 +31,47 @@ def allreduce_gram(pack: torch.Tensor, group=None) -> torch.Tensor:
     return pack
 
 
+class NcclGramReducer:
+    """The Gram all-reduce through the library's own C entry point (rbm_allreduce_gram) on a communicator created from a
+    unique id that is broadcast with torch.distributed.  Equivalent to `allreduce_gram`; exists so that applications
+    binding the C ABI directly (no torch collectives) have the complete path.  Must be constructed collectively."""
+
+    def __init__(self, device: int, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self._lib = _lib.load()
+        self._check = _lib.check
+        if not self._lib.rbm_nccl_available():
+            raise _lib.RbmNcclError(_lib.last_error())
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            self._check(self._lib.rbm_nccl_unique_id(buf), "rbm_nccl_unique_id")
+        box = [bytes(buf)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        comm = C.c_void_p()
+        self._check(self._lib.rbm_nccl_comm_create(idbuf, world, rank, int(device), C.byref(comm)), "rbm_nccl_comm_create")
+        self._comm = comm
+        self.device = int(device)
+
+    def __call__(self, pack: torch.Tensor) -> torch.Tensor:
+        import ctypes as C
+
+        if pack.numel() != 112 or pack.dtype != torch.float64 or not pack.is_cuda or not pack.is_contiguous():
+            raise ValueError("pack must be a contiguous CUDA tensor of 112 float64 values")
+        stream = C.c_void_p(torch.cuda.current_stream(pack.device).cuda_stream)
+        self._check(self._lib.rbm_allreduce_gram(self._comm, C.c_void_p(pack.data_ptr()), stream), "rbm_allreduce_gram")
+        return pack
+
+    def close(self):
+        if getattr(self, "_comm", None):
+            self._lib.rbm_nccl_comm_destroy(self._comm)
+            self._comm = None
+
+
 def max_over_ranks(value: float, device=None, group=None) -> float:
     """Max of a host scalar over ranks (timing convention: device time, max over ranks)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
