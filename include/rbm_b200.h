@@ -145,7 +145,7 @@ RBM_API int rbm_regressor_from_traj_f32(const rbm_model* m, const float* q, cons
  *   f [6][ld]: measured wrench per sample in the sensor frame.
  *   workspace: device scratch of rbm_gram_workspace_bytes() bytes (per-block partial sums; no atomics, the
  *   reduction order is fixed, so results are bit-reproducible for a given n).
- * The fp32 entry point reads float inputs, forms the regressor in float and accumulates in double every 16 samples. */
+ * The fp32 entry point reads float inputs, forms the regressor in float and accumulates in double every 64 samples. */
 RBM_API size_t rbm_gram_workspace_bytes(const rbm_model* m, int64_t n);
 RBM_API int rbm_regressor_gram_f64(const rbm_model* m, const double* q, const double* qd, const double* qdd, const double* f, double* gram_pack,
                            void* workspace, size_t workspace_bytes, int64_t n, int64_t ld, void* stream);

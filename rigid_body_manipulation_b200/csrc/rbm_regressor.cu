@@ -9,6 +9,8 @@
 // non-zero entries of the two diagonal blocks in registers, blocks reduce with warp shuffles + shared
 // memory, and a second single-block kernel sums the per-block partials in a FIXED order (deterministic
 // result for a given grid).  HBM traffic per sample: q, qd, qdd, f = 24 scalars read, nothing written.
+#include <cstdlib>
+
 #include "rbm_async.cuh"
 #include "rbm_internal.h"
 #include "rbm_rnea.cuh"
@@ -220,7 +222,7 @@ __device__ __forceinline__ void gram_block_epilogue(T (&acc)[kAcc], double (*red
   }
 }
 
-constexpr int kFlush = 16;  // fp32: samples accumulated in float registers between flushes into double
+constexpr int kFlush = 64;  // fp32: samples accumulated in float registers between flushes into double (rel. error ~64 * 2^-24)
 
 // ---- simple variant: direct global loads (any kernel path, any alignment) ----------------------------------
 template <class T, int PATH>
@@ -287,13 +289,17 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* buf = reinterpret_cast<T*>(smem_raw);  // [S][kStreams][kGramBlock]
   __shared__ __align__(8) uint64_t full[S];
+  __shared__ int drained[S];  // warps that have copied their samples of the stage's current tile into registers
   __shared__ double red[kGramBlock / 32][kAcc];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t nfull = n / kGramBlock;  // tiles moved by bulk copies; a ragged tail tile is read directly
   for (int k = lane; k < kAcc; k += 32) red[warp][k] = 0.0;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      drained[s] = 0;
+    }
     mbar_init_fence();
   }
   __syncthreads();
@@ -336,8 +342,17 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
       rqdd[k] = src[(12 + k) * kGramBlock];
       fs[k] = src[(18 + k) * kGramBlock];
     }
-    __syncthreads();               // every thread holds its sample in registers: the stage can be refilled
-    if (tid == 0) issue(it + S);
+    // No block-wide barrier: each warp announces that its 32 samples are in registers, and whichever warp arrives LAST
+    // refills the stage.  The warps of the CTA therefore drift apart and overlap each other's phases.
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      if (atomicAdd(&drained[st], 1) == kGramBlock / 32 - 1) {
+        drained[st] = 0;
+        __threadfence_block();
+        issue(it + S);
+      }
+    }
     gram_sample_fast<T, PATH>(P, rq, rqd, rqdd, fs, acc);
     if constexpr (sizeof(T) == 4) {
       if (++since_flush == kFlush) {
@@ -457,10 +472,11 @@ int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* 
   if (n > 0) {
     // bulk copies need 16-byte aligned rows: base pointers and the row pitch
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    const bool tma_ok = sizeof(T) == 4 && m->path != PATH_GENERIC && al16(q) && al16(qd) && al16(qdd) && al16(f) && ((ld * sizeof(T)) % 16 == 0) && n >= kGramBlock &&
+    static const bool tma_f64 = [] { const char* e = getenv("RBM_GRAM_TMA_F64"); return e && e[0] == '1'; }();  // experiment knob
+    const bool tma_ok = (sizeof(T) == 4 || tma_f64) && m->path != PATH_GENERIC && al16(q) && al16(qd) && al16(qdd) && al16(f) && ((ld * sizeof(T)) % 16 == 0) && n >= kGramBlock &&
                         !m->no_tma;
     if (tma_ok) {
-      grid = gram_grid(m, n, 2);  // 119 registers, 96 KB of stages: two CTAs per SM
+      grid = gram_grid(m, n, sizeof(T) == 4 ? 2 : 1);  // fp32: 119 registers, 96 KB of stages: two CTAs per SM
       constexpr size_t smem = (size_t)kGramStages * kStreams * kGramBlock * sizeof(T);
       static bool attr_set = false;  // idempotent; set once per (T) instantiation and process
       if (!attr_set) {

@@ -72,3 +72,56 @@ def sensor_frame_params(target, pose_sen_obj_Rt) -> np.ndarray:
     c = R @ target.com + t
     I0 = R @ target.inertia_com @ R.T + target.mass * (c @ c * np.eye(3) - np.outer(c, c))
     return np.array([target.mass, *(target.mass * c), I0[0, 0], I0[1, 1], I0[2, 2], I0[0, 1], I0[1, 2], I0[2, 0]])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dataset handling around the solve (reference loggers/loggers.py:82-156, core/simulate.py:281-290)
+# ---------------------------------------------------------------------------------------------------------------
+def split_indices(n: int, valid_ratio: float = 0.1, test_ratio: float = 0.1, seed: int = 0):
+    """Frame indices of the train / valid / test subsets exactly as the reference's `Logger._split` draws them
+    (loggers.py:94-106): one `default_rng(seed).shuffle` of range(n); train = the first n - n_test - n_valid, valid = the
+    next n_valid -- and `test` is the SAME slice as valid (the reference slices [num_train : num_train + num_valid] twice,
+    loggers.py:105-106; reproduced, not fixed)."""
+    num_test = int(n * test_ratio)
+    num_valid = int(n * valid_ratio)
+    num_train = n - num_test - num_valid
+    order = list(range(n))
+    np.random.default_rng(seed).shuffle(order)
+    order = np.asarray(order, dtype=np.int64)
+    valid = order[num_train : num_train + num_valid]
+    return order[:num_train], valid, valid.copy()
+
+
+def perturb_wrench(fts, error_rate: float = 0.05, seed: int = 0):
+    """The reference's measurement-noise model (core/simulate.py:281-290): zero-mean Gaussian noise on forces and on torques
+    with sigma = error_rate * max_frames ||force|| (resp. ||torque||), one generator seeded `seed`, forces drawn first.
+    fts: (n, 6) host array [force; torque]; returns a perturbed copy."""
+    fts = np.array(fts, dtype=np.float64, copy=True)
+    rng = np.random.default_rng(seed)
+    fs_std = error_rate * np.linalg.norm(fts[..., :3], axis=1).max()
+    ts_std = error_rate * np.linalg.norm(fts[..., 3:], axis=1).max()
+    fts[..., :3] += fs_std * rng.standard_normal((len(fts), 3))
+    fts[..., 3:] += ts_std * rng.standard_normal((len(fts), 3))
+    return fts
+
+
+def identify_splits(model, q, qd, qdd, f, valid_ratio: float = 0.1, test_ratio: float = 0.1, seed: int = 0, reduce=None) -> dict:
+    """`Logger.finish` (loggers.py:147-156) on the device: identification on all frames and on the train / valid / test
+    subsets.  q, qd, qdd, f are CUDA tensors (nj, n) / (6, n); `reduce` is an optional callable applied to every Gram pack
+    (e.g. distributed.allreduce_gram when the frames are sharded)."""
+    import torch
+
+    n = q.shape[1]
+    out = {}
+    subsets = dict(zip(("train", "valid", "test"), split_indices(n, valid_ratio, test_ratio, seed)))
+    for name, idx in [("all", None)] + list(subsets.items()):
+        if idx is None:
+            args = (q, qd, qdd, f)
+        else:
+            sel = torch.as_tensor(idx, device=q.device)
+            args = tuple(t.index_select(1, sel).contiguous() for t in (q, qd, qdd, f))
+        pack = model.regressor_gram(*args).clone()
+        if reduce is not None:
+            reduce(pack)
+        out[name] = solve(pack)
+    return out

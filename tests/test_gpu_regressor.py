@@ -153,3 +153,35 @@ def test_gram_linearity_checksum_at_full_size():
     diff = (whole - (a + b)).abs().max().item()
     assert diff < 1e-10 * whole.abs().max().item()
     assert whole[111].item() == n
+
+
+def test_config1_identification_pipeline():
+    """The reference's end-of-run identification (loggers.py:110-156) on the open-loop config-1 data: regressors at the 151 frame
+    steps of the base.yaml trajectory, wrench = Y phi + the reference's 5 % noise, lstsq on all / train / valid / test."""
+    g = load_golden("ref_inverse_hammer.npz")
+    c1 = load_golden("ref_config1_hammer.npz")
+    m = model_from_golden(g)
+    steps = c1["frame_steps"]
+    traj = c1["traj"][steps]
+    Y = c1["regressor_frames"]
+    # ground truth of the object in the sensor frame from the folded inertia
+    from rigid_body_manipulation_b200 import model as rbm_model
+
+    c = rbm_model.load_packaged("sequential", "hammer")
+    phi_true = identification.sensor_frame_params(c.target, c.pose_sen_obj_Rt)
+    f_clean = Y @ phi_true
+    f_noisy = identification.perturb_wrench(f_clean)
+    q, qd, qdd = soa(traj)
+    fd = torch.as_tensor(f_noisy, device="cuda").t().contiguous()
+    res = identification.identify_splits(m, q, qd, qdd, fd)
+    tr, va, te = identification.split_indices(len(steps))
+    for name, idx in (("all", np.arange(len(steps))), ("train", tr), ("valid", va), ("test", te)):
+        ref = rv.identify_lstsq(Y[idx], f_noisy[idx])  # np.linalg.lstsq on the stacked regressor (loggers.py:127-129)
+        got = res[name]
+        assert got.n_samples == len(idx)
+        # normal equations square the condition number: agreement scales with cond * eps
+        assert np.abs(got.phi - ref).max() < 1e-8 * max(1.0, np.abs(ref).max()) * max(1.0, got.cond * 1e-6), (name, got.cond)
+    assert np.array_equal(res["valid"].phi, res["test"].phi)
+    # noise-free: exact recovery of the CAD parameters expressed in the sensor frame
+    clean = identification.solve(m.regressor_gram(q, qd, qdd, torch.as_tensor(f_clean, device="cuda").t().contiguous()))
+    assert np.abs(clean.phi - phi_true).max() < 1e-6 * max(1.0, clean.cond * 1e-6)

@@ -121,3 +121,31 @@ def test_shard_ranges_partition_the_batch():
         assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         distributed.shard_range(10, 3, 3)
+
+
+def test_split_and_noise_follow_the_reference_recipes():
+    """loggers.py:82-108 (`_split`, including its test == valid slice) and simulate.py:281-290 (5 % noise, seed 0)."""
+    from operator import itemgetter
+
+    n = 151  # base.yaml: 50 fps x 3 s + 1 frames
+    tr, va, te = identification.split_indices(n)
+    # literal restatement of the reference method on a list
+    data = list(range(n))
+    rng = np.random.default_rng(0)
+    idx = list(range(n))
+    rng.shuffle(idx)
+    num_test, num_valid = int(n * 0.1), int(n * 0.1)
+    num_train = n - num_test - num_valid
+    assert list(tr) == list(itemgetter(*idx[:num_train])(data))
+    assert list(va) == list(itemgetter(*idx[num_train : num_train + num_valid])(data))
+    assert list(te) == list(va)  # the reference's quirk
+    assert len(set(tr) & set(va)) == 0 and len(tr) + len(va) + num_test == n
+    f = np.random.default_rng(3).standard_normal((n, 6)) * np.array([10, 10, 10, 1, 1, 1.0])
+    g = identification.perturb_wrench(f)
+    r = np.random.default_rng(0)
+    fs = 0.05 * np.linalg.norm(f[:, :3], axis=1).max()
+    ts = 0.05 * np.linalg.norm(f[:, 3:], axis=1).max()
+    exp = f.copy()
+    exp[:, :3] += fs * r.standard_normal((n, 3))
+    exp[:, 3:] += ts * r.standard_normal((n, 3))
+    assert np.array_equal(g, exp) and not np.shares_memory(g, f)
