@@ -179,3 +179,101 @@ def test_planned_trajectory_kernel_matches_config1(force_generic):
     assert rel_err(tau10.t().cpu().numpy(), c1["tau"][::10]).max() < TOL64
     tau32 = m.rnea_planned(plan, dtype=torch.float32)
     assert rel_err(tau32.t().cpu().numpy(), c1["tau"]).max() < TOL32  # the profile itself is evaluated in double in both modes
+
+
+def test_fast_and_generic_kernels_agree_at_scale():
+    """The structure-specialised kernel (snapped 0 / +-1 pattern, rigid-body inertia parameters) and the generic kernel (dense
+    constants exactly as given) are two independent evaluations of the same model: 2^20 samples, agreement to round-off."""
+    g = load_golden("ref_inverse_kill_la_kill.npz")  # strongly off-axis object
+    fast, generic = model_from_golden(g), model_from_golden(g, force_generic=True)
+    assert fast.kernel_path == "seq_iso" and generic.kernel_path == "generic"
+    q, qd, qdd = soa(sample_states(np.random.default_rng(8), 1 << 20))
+    a, b = fast.rnea(q, qd, qdd), generic.rnea(q, qd, qdd)
+    scale = b.abs().amax(dim=0).clamp_min(1e-6)
+    assert ((a - b).abs().amax(dim=0) / scale).max().item() < 1e-12
+
+
+def test_rigid_variant_of_the_fast_path():
+    """Same kinematic structure with non-isotropic link inertias selects the SEQ_RIGID kernel; checked against the C oracle."""
+    from oracle import build_c
+    from rigid_body_manipulation_b200.engine import Model
+
+    g = load_golden("ref_inverse_hammer.npz")
+    sim = g["simats"].copy()
+    rng = np.random.default_rng(5)
+    for k in range(1, 6):  # give links 1-5 an offset centre of mass and a full inertia tensor (still a physical rigid body)
+        m, c = 8.0 + k, rng.uniform(-0.1, 0.1, 3)
+        A = rng.standard_normal((3, 3)) * 0.1
+        Ic = A @ A.T + 0.05 * np.eye(3)
+        cx = np.array([[0, -c[2], c[1]], [c[2], 0, -c[0]], [-c[1], c[0], 0]])
+        sim[k] = np.block([[m * np.eye(3), -m * cx], [m * cx, Ic + m * (c @ c * np.eye(3) - np.outer(c, c))]])
+    mdl = Model(g["hposes_Rt"], sim, g["uscrews"], g["twist_0"], g["dtwist_0"])
+    assert mdl.kernel_path == "seq_rigid"
+    traj = sample_states(rng, 5000)
+    ref = build_c.inverse_batched_c(traj, g["hposes_Rt"], sim, g["uscrews"], g["twist_0"], g["dtwist_0"])
+    q, qd, qdd = soa(traj)
+    assert rel_err(mdl.rnea(q, qd, qdd).t().cpu().numpy(), ref).max() < TOL64
+    # a model that breaks the structure (tilted home rotation) must fall back to the generic kernel, not be snapped
+    h = g["hposes_Rt"].copy()
+    th = 1e-6
+    Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    h[2, :9] = (Rz @ h[2, :9].reshape(3, 3)).reshape(9)
+    tilted = Model(h, g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"])
+    assert tilted.kernel_path == "generic"
+    ref = build_c.inverse_batched_c(traj, h, g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"])
+    assert rel_err(tilted.rnea(q, qd, qdd).t().cpu().numpy(), ref).max() < TOL64
+
+
+def test_extreme_inputs():
+    """Huge joint angles exercise the slow (Payne-Hanek) path of the device sincos; non-finite inputs must propagate, not crash."""
+    from oracle import build_c
+
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    rng = np.random.default_rng(2)
+    traj = sample_states(rng, 4096)
+    traj[:, 0, 3:] = rng.uniform(-1, 1, (4096, 3)) * 10.0 ** rng.uniform(3, 9, (4096, 3))
+    ref = build_c.inverse_batched_c(traj, g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"])
+    q, qd, qdd = soa(traj)
+    assert rel_err(m.rnea(q, qd, qdd).t().cpu().numpy(), ref).max() < TOL64
+    traj[7, 0, 4] = np.inf
+    traj[9, 2, 1] = np.nan
+    q, qd, qdd = soa(traj)
+    tau = m.rnea(q, qd, qdd).t().cpu().numpy()
+    assert np.isnan(tau[7]).any() and np.isnan(tau[9]).any()
+    keep = np.ones(4096, bool)
+    keep[[7, 9]] = False
+    assert rel_err(tau[keep], ref[keep]).max() < TOL64
+
+
+def test_maximum_size_property_fp32():
+    """Largest single-launch batch used in the configs[4] sweep that fits beside its outputs (2^28 fp32 samples = 25.8 GB of
+    inputs): size-independent property -- tau is affine in qdd -- checked on the device, plus a spot parity check."""
+    from oracle import build_c
+
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    n = 1 << 28
+    if torch.cuda.mem_get_info()[0] < 60e9:
+        pytest.skip("not enough free HBM")
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    q = torch.empty((6, n), dtype=torch.float32, device="cuda")
+    q[:3] = torch.rand((3, n), generator=gen, device="cuda") * 4 - 1.5
+    q[3:] = (torch.rand((3, n), generator=gen, device="cuda") * 2 - 1) * 6 * np.pi
+    qd = torch.randn((6, n), generator=gen, device="cuda")
+    qdd = torch.randn((6, n), generator=gen, device="cuda") * 3
+    t1 = m.rnea(q, qd, qdd)
+    idx = torch.randint(0, n, (4096,), device="cuda")
+    traj = torch.stack([q[:, idx].t(), qd[:, idx].t(), qdd[:, idx].t()], dim=1).double().cpu().numpy()
+    ref = build_c.inverse_batched_c(traj, g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"])
+    assert rel_err(t1[:, idx].t().cpu().numpy(), ref).max() < TOL32
+    last = torch.arange(n - 300, n, device="cuda")  # the ragged end of the grid
+    trajl = torch.stack([q[:, last].t(), qd[:, last].t(), qdd[:, last].t()], dim=1).double().cpu().numpy()
+    refl = build_c.inverse_batched_c(trajl, g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"])
+    assert rel_err(t1[:, last].t().cpu().numpy(), refl).max() < TOL32
+    qdd.mul_(2.0)
+    t2 = m.rnea(q, qd, qdd)
+    qdd.zero_()
+    t0 = m.rnea(q, qd, qdd)
+    lin = (t2 - t1).sub_(t1).add_(t0).abs_().amax().item()
+    assert lin < 2e-4 * t1.abs().amax().item()
