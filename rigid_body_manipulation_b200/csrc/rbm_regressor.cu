@@ -269,12 +269,15 @@ __global__ void __launch_bounds__(kGramBlock, 1) k_regressor_gram(const __grid_c
   gram_block_epilogue<T>(acc, red, partials);
 }
 
-// ---- pipelined variant (fast paths, fp32 mode): TMA bulk copies stage whole 256-sample tiles of the 24 input streams
-// (24 x 1 KB) into shared memory kGramStages tiles ahead of the arithmetic, so the loads never wait on registers or
-// occupancy.  Measured on B200 (round 1, 12.5 M samples): fp32 25.0 -> 34.9 G samples/s against the direct-load kernel; in
-// fp64 the kernel is FP64-pipe/latency-bound at 8 warps per SM and the direct-load kernel is as fast (22.9 vs 22.0), so fp64
-// keeps the simple variant.  A per-warp pipeline with 256-byte bulk copies was tried and rejected (TMA issue-bound on the
-// 24 tiny copies per 32 samples: 17.6 / 26.5 G samples/s). -------------------------------------------------------------
+// ---- pipelined variant (fast paths): TMA bulk copies stage whole 256-sample tiles of the 24 input streams (24 x 2 KB in
+// fp64) into shared memory kGramStages tiles ahead of the arithmetic, so the loads never wait on registers or occupancy.
+// What was measured on B200 while getting here (round 1, 12.5 M samples, G samples/s fp64 / fp32):
+//   direct global loads                                   23.6 / 25.0   (41 % of stall samples on the load scoreboard)
+//   TMA, one elected thread issues all 24 copies          21.8 / 34.9   (the issuing warp pays ~24 x UBLKCP per tile)
+//   same + "last warp to drain refills" instead of a CTA barrier   20.8 / 34.6   (the barrier was not the limiter)
+//   per-warp pipelines with 256-byte copies               17.6 / 26.5   (8x more copies: TMA-issue bound)
+//   TMA, the 24 copies spread over the 8 warps (this code) 23.9 / 42.6
+// In fp64 the kernel is then bound by the FP64 pipe at 8 warps per SM (250 registers: 70 double accumulators).
 constexpr int kStreams = 24;  // q(6) qd(6) qdd(6) f(6)
 constexpr int kGramStages = 4;
 
@@ -297,30 +300,31 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], kGramBlock / 32);  // one arrive.expect_tx per warp (each brings its share of the 24 copies)
       drained[s] = 0;
     }
     mbar_init_fence();
   }
   __syncthreads();
 
-  auto issue = [&](int64_t it) {  // one elected thread: 24 bulk copies of one tile into stage it % S
+  // Issue cost of a bulk copy is paid by the issuing warp, so the 24 copies of a tile are spread over the 8 warps: lane 0 of
+  // warp w brings streams w, w + 8, w + 16 and announces their bytes on the stage's barrier.
+  const T* const stream_base[4] = {q, qd, qdd, f};
+  auto issue = [&](int64_t it) {
     const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
     if (tile >= nfull) return;
     const int st = (int)(it % S);
     uint64_t* bar = &full[st];
-    mbar_arrive_expect_tx(bar, kTileBytes);
+    mbar_arrive_expect_tx(bar, 3 * kRowBytes);
     T* dst = buf + (size_t)st * kStreams * kGramBlock;
     const int64_t s0 = tile * kGramBlock;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      bulk_copy_g2s(dst + k * kGramBlock, q + k * ld + s0, kRowBytes, bar);
-      bulk_copy_g2s(dst + (6 + k) * kGramBlock, qd + k * ld + s0, kRowBytes, bar);
-      bulk_copy_g2s(dst + (12 + k) * kGramBlock, qdd + k * ld + s0, kRowBytes, bar);
-      bulk_copy_g2s(dst + (18 + k) * kGramBlock, f + k * ld + s0, kRowBytes, bar);
+    for (int i = 0; i < 3; ++i) {
+      const int k = warp + 8 * i;  // stream index 0..23 = array (k / 6), row (k % 6)
+      bulk_copy_g2s(dst + k * kGramBlock, stream_base[k / 6] + (int64_t)(k % 6) * ld + s0, kRowBytes, bar);
     }
   };
-  if (tid == 0) {
+  if (lane == 0) {
     for (int it = 0; it < S; ++it) issue(it);
   }
 
@@ -342,17 +346,8 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
       rqdd[k] = src[(12 + k) * kGramBlock];
       fs[k] = src[(18 + k) * kGramBlock];
     }
-    // No block-wide barrier: each warp announces that its 32 samples are in registers, and whichever warp arrives LAST
-    // refills the stage.  The warps of the CTA therefore drift apart and overlap each other's phases.
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      if (atomicAdd(&drained[st], 1) == kGramBlock / 32 - 1) {
-        drained[st] = 0;
-        __threadfence_block();
-        issue(it + S);
-      }
-    }
+    __syncthreads();               // every thread holds its sample in registers: the stage can be refilled
+    if (lane == 0) issue(it + S);  // each warp re-issues its three streams
     gram_sample_fast<T, PATH>(P, rq, rqd, rqdd, fs, acc);
     if constexpr (sizeof(T) == 4) {
       if (++since_flush == kFlush) {
@@ -472,8 +467,7 @@ int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* 
   if (n > 0) {
     // bulk copies need 16-byte aligned rows: base pointers and the row pitch
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    static const bool tma_f64 = [] { const char* e = getenv("RBM_GRAM_TMA_F64"); return e && e[0] == '1'; }();  // experiment knob
-    const bool tma_ok = (sizeof(T) == 4 || tma_f64) && m->path != PATH_GENERIC && al16(q) && al16(qd) && al16(qdd) && al16(f) && ((ld * sizeof(T)) % 16 == 0) && n >= kGramBlock &&
+    const bool tma_ok = m->path != PATH_GENERIC && al16(q) && al16(qd) && al16(qdd) && al16(f) && ((ld * sizeof(T)) % 16 == 0) && n >= kGramBlock &&
                         !m->no_tma;
     if (tma_ok) {
       grid = gram_grid(m, n, sizeof(T) == 4 ? 2 : 1);  // fp32: 119 registers, 96 KB of stages: two CTAs per SM

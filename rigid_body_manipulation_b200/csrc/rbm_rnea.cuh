@@ -6,6 +6,7 @@
 //   generic path: generic_rnea<T, NJ>()  -- any model, parameters read from shared memory.
 #pragma once
 #include "rbm_model.cuh"
+#include "rbm_trig.cuh"
 #include "rbm_typed.cuh"
 
 namespace rbm {
@@ -148,21 +149,29 @@ struct FastResult {
   T v[3], w[3], a[3], l[3];  // twist and twist rate of the last link (V_6, dV_6)
 };
 
-template <class T> RBM_HD void sincos_t(T x, T* s, T* c);
-template <> RBM_HD void sincos_t<double>(double x, double* s, double* c) { sincos(x, s, c); }
-template <> RBM_HD void sincos_t<float>(float x, float* s, float* c) { sincosf(x, s, c); }
+template <class T> RBM_HD void sincos_t(T x, T* s, T* c) { sincos_one(x, s, c); }  // rbm_trig.cuh
 
-// sin / cos of the revolute joint angles of descriptor D (prismatic entries stay c = 1, s = 0)
+// sin / cos of the revolute joint angles of descriptor D (prismatic entries stay c = 1, s = 0); the angles are evaluated as
+// one group so that their polynomial chains interleave (rbm_trig.cuh)
 template <class T, class D>
 RBM_HD void fast_sincos(const T (&q)[6], T (&c)[6], T (&s)[6]) {
+  constexpr bool hinge[6] = {D::L0::jk == JOINT_RZ, D::L1::jk == JOINT_RZ, D::L2::jk == JOINT_RZ,
+                             D::L3::jk == JOINT_RZ, D::L4::jk == JOINT_RZ, D::L5::jk == JOINT_RZ};
+  constexpr int NH = hinge[0] + hinge[1] + hinge[2] + hinge[3] + hinge[4] + hinge[5];
 #pragma unroll
   for (int i = 0; i < 6; ++i) { c[i] = T(1); s[i] = T(0); }
-  if constexpr (D::L0::jk == JOINT_RZ) sincos_t(q[0], &s[0], &c[0]);
-  if constexpr (D::L1::jk == JOINT_RZ) sincos_t(q[1], &s[1], &c[1]);
-  if constexpr (D::L2::jk == JOINT_RZ) sincos_t(q[2], &s[2], &c[2]);
-  if constexpr (D::L3::jk == JOINT_RZ) sincos_t(q[3], &s[3], &c[3]);
-  if constexpr (D::L4::jk == JOINT_RZ) sincos_t(q[4], &s[4], &c[4]);
-  if constexpr (D::L5::jk == JOINT_RZ) sincos_t(q[5], &s[5], &c[5]);
+  if constexpr (NH > 0) {
+    T x[NH], sn[NH], cs[NH];
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (hinge[i]) x[k++] = q[i];
+    sincos_group<NH, T>(x, sn, cs);
+    k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (hinge[i]) { s[i] = sn[k]; c[i] = cs[k]; ++k; }
+  }
 }
 
 template <class T, class D, bool WANT_TAU, bool VEL = true, bool GRAV = true>

@@ -72,8 +72,9 @@ def _gram_reference(g, traj, f):
 @pytest.mark.parametrize("n", [1, 255, 4096, 100_003, 100_352, 300_002])
 @pytest.mark.parametrize("no_tma", [False, True])
 def test_gram_matches_materialised_normal_equations(fname, n, no_tma):
-    """fp64 always takes the direct-load kernel (the TMA-pipelined variant is used in fp32 mode only, see
-    test_gram_fp32_mode); sizes cover single-CTA, multi-wave and ragged-tail cases for fast and generic models."""
+    """Aligned batches of >= 256 samples on the fast path take the TMA-pipelined kernel (4096, 100_352, and 300_002 with its
+    ragged 226-sample tail); odd n (row pitch not 16-byte aligned), tiny n, generic models and no_tma=True take the direct-load
+    kernel.  Both must agree with the materialised normal equations."""
     g = load_golden(fname)
     m = model_from_golden(g, no_tma=no_tma)
     nj = m.nj

@@ -54,13 +54,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-exp", type=int, default=9)
     ap.add_argument("--out", default="")
+    ap.add_argument("--generic", action="store_true", help="force the generic (any-model) kernel")
+    ap.add_argument("--min-exp", type=int, default=4)
     args = ap.parse_args()
     c = rbm_model.load_packaged("sequential", "hammer")
-    m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0)
+    m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, force_generic=args.generic)
     free_b = torch.cuda.mem_get_info()[0]
     lines = []
     for name, dt, es in (("f32", torch.float32, 4), ("f64", torch.float64, 8)):
-        for e in range(4, args.max_exp + 1):
+        for e in range(args.min_exp, args.max_exp + 1):
             B = 10**e
             alg = 24 * es * B
             nset = 1 if alg > 8 * L2 else int(np.ceil(3 * L2 / alg)) + 1
@@ -87,7 +89,7 @@ def main():
 
             pms = timed(pstep)
             gbs = alg / (ms * 1e-3) / 1e9
-            lines.append({"dtype": name, "B": B, "ms": ms, "samples_per_s": B / (ms * 1e-3), "GBps_algorithmic": gbs, "frac_of_measured_hbm": gbs / PEAK,
+            lines.append({"kernel_path": m.kernel_path, "dtype": name, "B": B, "ms": ms, "samples_per_s": B / (ms * 1e-3), "GBps_algorithmic": gbs, "frac_of_measured_hbm": gbs / PEAK,
                           "buffer_sets": nset, "planned_ms": pms, "planned_samples_per_s": B / (pms * 1e-3),
                           "planned_GBps_algorithmic": 6 * es * B / (pms * 1e-3) / 1e9})
             print(json.dumps(lines[-1]), flush=True)
