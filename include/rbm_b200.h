@@ -101,6 +101,11 @@ RBM_API int rbm_rnea_aos_f32(const rbm_model* m, const float* traj, float* tau, 
 RBM_API int rbm_rnea_full_f64(const rbm_model* m, const double* traj, double* tau, double* poses, double* twists, double* dtwists,
                       int64_t n, void* stream);
 
+/* The same with HOST buffers, for small batches (the scalar drop-in `dynamics.inverse` calls it with n = 1): one host->device
+ * copy, one launch, one device->host copy through scratch owned by the model; synchronous.  poses / twists+dtwists may be NULL. */
+RBM_API int rbm_rnea_full_host_f64(const rbm_model* m, const double* traj_host, double* tau_host, double* poses_host, double* twists_host,
+                           double* dtwists_host, int64_t n);
+
 /* Planner-driven inverse dynamics: the quintic rest-to-rest trajectory of planners/joint_position_planner.py:86-131
  * (traj_5th_spline) is evaluated inside the kernel, so nothing is read from HBM.  Sample s is step k = step0 + s*stride:
  *   prof = coeffs . [k^5 .. 1];  q_j = disp_j prof + offset_j;  qd_j = disp_j prof' / timestep;  qdd_j = disp_j prof'' / timestep^2

@@ -54,6 +54,7 @@ SIGNATURES = {
     "rbm_rnea_aos_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rbm_rnea_aos_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rbm_rnea_full_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "rbm_rnea_full_host_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "rbm_rnea_planned_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double, _vp, _vp, _i64, _i64, _vp]),
     "rbm_rnea_planned_f32": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double, _vp, _vp, _i64, _i64, _vp]),
     "rbm_rnea_host_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64]),

@@ -257,6 +257,8 @@ int rbm_model_create(int nj, const double* hposes_Rt, const double* simats, cons
 
 void rbm_model_destroy(rbm_model* m) {
   if (!m) return;
+  if (m->full_dev) cudaFree(m->full_dev);
+  if (m->full_pinned) cudaFreeHost(m->full_pinned);
   for (int k = 0; k < rbm_model::kPipeSlots; ++k) {
     if (m->pipe_st[k]) cudaStreamDestroy(m->pipe_st[k]);
     if (m->pipe_in[k]) cudaFree(m->pipe_in[k]);
@@ -338,6 +340,49 @@ int rbm_rnea_host_f32(const rbm_model* m, const float* traj_host, float* tau_hos
   return rnea_host<float>(m, traj_host, tau_host, n, chunk);
 }
 
+
+// Small-batch host convenience behind the scalar drop-in `dynamics.inverse`: host traj in, every output of the reference's
+// return value out, with one H2D copy, one launch and one D2H copy through scratch owned by the model.
+int rbm_rnea_full_host_f64(const rbm_model* m, const double* traj_host, double* tau_host, double* poses_host, double* twists_host,
+                           double* dtwists_host, int64_t n) {
+  RBM_CHECK_BATCH("rbm_rnea_full_host_f64")
+  if (!traj_host || !tau_host) return invalid("rbm_rnea_full_host_f64: NULL buffer");
+  if ((twists_host == nullptr) != (dtwists_host == nullptr)) return invalid("rbm_rnea_full_host_f64: twists and dtwists go together");
+  const int nj = m->nj;
+  const size_t n_in = (size_t)n * 3 * nj, n_tau = (size_t)n * nj, n_pose = (size_t)n * nj * 12, n_tw = (size_t)n * (nj + 1) * 6;
+  const size_t total = n_in + n_tau + n_pose + 2 * n_tw;
+  RBM_CUDA_TRY(cudaSetDevice(m->device));
+  std::lock_guard<std::mutex> lock(m->pipe_mu);
+  if (total > m->full_doubles) {
+    if (m->full_dev) cudaFree(m->full_dev);
+    if (m->full_pinned) cudaFreeHost(m->full_pinned);
+    m->full_dev = nullptr;
+    m->full_pinned = nullptr;
+    m->full_doubles = 0;
+    const size_t cap = total < 4096 ? 4096 : total;
+    RBM_CUDA_TRY(cudaMalloc(&m->full_dev, cap * sizeof(double)));
+    RBM_CUDA_TRY(cudaMallocHost(&m->full_pinned, cap * sizeof(double)));
+    m->full_doubles = cap;
+  }
+  if (!m->pipe_st[0]) RBM_CUDA_TRY(cudaStreamCreateWithFlags(&m->pipe_st[0], cudaStreamNonBlocking));
+  cudaStream_t st = m->pipe_st[0];
+  double* d_in = m->full_dev;
+  double* d_out = m->full_dev + n_in;
+  std::memcpy(m->full_pinned, traj_host, n_in * sizeof(double));
+  RBM_CUDA_TRY(cudaMemcpyAsync(d_in, m->full_pinned, n_in * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = launch_rnea_full<double>(m, d_in, d_out, d_out + n_tau, d_out + n_tau + n_pose, d_out + n_tau + n_pose + n_tw, n, st);
+  if (rc != RBM_OK) return rc;
+  double* h_out = m->full_pinned + n_in;
+  RBM_CUDA_TRY(cudaMemcpyAsync(h_out, d_out, (total - n_in) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RBM_CUDA_TRY(cudaStreamSynchronize(st));
+  std::memcpy(tau_host, h_out, n_tau * sizeof(double));
+  if (poses_host) std::memcpy(poses_host, h_out + n_tau, n_pose * sizeof(double));
+  if (twists_host) {
+    std::memcpy(twists_host, h_out + n_tau + n_pose, n_tw * sizeof(double));
+    std::memcpy(dtwists_host, h_out + n_tau + n_pose + n_tw, n_tw * sizeof(double));
+  }
+  return RBM_OK;
+}
 
 // ---- regressor / identification ------------------------------------------------------------------
 int rbm_regressor_rows_f64(const double* twists, const double* dtwists, double* Y, int64_t n, void* stream) {

@@ -28,6 +28,10 @@ struct rbm_model {
   mutable void* pipe_in[kPipeSlots] = {nullptr, nullptr, nullptr};
   mutable void* pipe_out[kPipeSlots] = {nullptr, nullptr, nullptr};
   mutable size_t pipe_in_bytes = 0, pipe_out_bytes = 0;
+  // scratch of the small-batch host entry point rbm_rnea_full_host_f64 (device + pinned host mirror)
+  mutable double* full_dev = nullptr;
+  mutable double* full_pinned = nullptr;
+  mutable size_t full_doubles = 0;
 };
 
 namespace rbm {

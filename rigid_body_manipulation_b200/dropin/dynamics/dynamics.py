@@ -2,7 +2,7 @@
 function evaluates on the GPU through librbm_b200.so (there is no CPU fallback: without a CUDA device the calls raise).
 
   reference symbol (dynamics/dynamics.py)            -> C ABI entry point
-  inverse :109-157                                    rbm_model_create + rbm_rnea_full_f64   (batched: rbm_rnea_*)
+  inverse :109-157                                    rbm_model_create + rbm_rnea_full_host_f64   (batched: rbm_rnea_*)
   transfer_simat :72-106                              rbm_transfer_simat_f64
   get_spatial_inertia_matrix :62-69                   rbm_spatial_inertia_f64
   get_regressor_matrix :215-249                       rbm_regressor_rows_f64
@@ -52,18 +52,24 @@ def make_model(hposes_body_parent, simats_body, uscrews_body, twist_0, dtwist_0,
     return _engine.Model(hposes_body_parent, simats_body, uscrews_body, twist_0, dtwist_0, wrench_tip, pose_tip_ee, pose_sen_llj, device)
 
 
+def _pose_key(p):
+    if hasattr(p, "rot"):
+        return np.asarray(p.rot.as_matrix(), dtype=np.float64).tobytes() + np.asarray(p.trans, dtype=np.float64).tobytes()
+    return np.asarray(p, dtype=np.float64).tobytes()
+
+
 def _cached_model(hposes_body_parent, simats_body, uscrews_body, twist_0, dtwist_0, wrench_tip, pose_tip_ee):
-    uscrews = np.ascontiguousarray(uscrews_body, dtype=np.float64)
-    Rt = _engine.poses_to_Rt(hposes_body_parent[: len(uscrews) + 1])
-    tipRt = _engine.pose_to_Rt(pose_tip_ee)
-    parts = (Rt, np.ascontiguousarray(simats_body, dtype=np.float64), uscrews, np.asarray(twist_0, dtype=np.float64),
-             np.asarray(dtwist_0, dtype=np.float64), np.asarray(wrench_tip, dtype=np.float64), tipRt)
-    key = (torch.cuda.current_device(),) + tuple(p.tobytes() for p in parts)
+    """Content-keyed lookup (a few microseconds of hashing per call; the arrays are mutable, so identity is not enough)."""
+    nj = len(uscrews_body)
+    key = (torch.cuda.current_device(), np.asarray(uscrews_body, dtype=np.float64).tobytes(), np.asarray(simats_body, dtype=np.float64).tobytes(),
+           np.asarray(twist_0, dtype=np.float64).tobytes(), np.asarray(dtwist_0, dtype=np.float64).tobytes(),
+           np.asarray(wrench_tip, dtype=np.float64).tobytes(), _pose_key(pose_tip_ee)) + tuple(_pose_key(h) for h in hposes_body_parent[: nj + 1])
     m = _MODELS.get(key)
     if m is None:
         if len(_MODELS) >= _MODELS_MAX:
             _MODELS.pop(next(iter(_MODELS)))
-        m = _MODELS[key] = _engine.Model(Rt, parts[1][: len(uscrews) + 1], uscrews, parts[3], parts[4], parts[5], tipRt)
+        m = _MODELS[key] = _engine.Model(_engine.poses_to_Rt(hposes_body_parent[: nj + 1]), np.asarray(simats_body, dtype=np.float64)[: nj + 1],
+                                         uscrews_body, twist_0, dtwist_0, wrench_tip, _engine.pose_to_Rt(pose_tip_ee))
     return m
 
 
@@ -198,16 +204,8 @@ def inverse(
     if traj.shape != (3, nj):
         raise ValueError(f"traj must have shape (3, {nj})")
     model = _cached_model(hposes_body_parent, simats_body, uscrews_body, twist_0, dtwist_0, wrench_tip, pose_tip_ee)
-    dev_traj = torch.as_tensor(np.ascontiguousarray(traj[None]), device=model.device)
-    tau, poses, tw, dtw = model.rnea_full(dev_traj)
-    packed = _np(torch.cat([tau.reshape(-1), poses.reshape(-1), tw.reshape(-1), dtw.reshape(-1)]))  # one D2H copy
-    o = nj
-    tau_h = packed[:o]
-    poses_h = packed[o : o + 12 * nj].reshape(nj, 12)
-    o += 12 * nj
-    tw_h = packed[o : o + 6 * (nj + 1)].reshape(nj + 1, 6)
-    o += 6 * (nj + 1)
-    dtw_h = packed[o:].reshape(nj + 1, 6)
+    tau, poses, tw, dtw = model.rnea_full_host(traj[None])  # one H2D, one launch, one D2H (rbm_rnea_full_host_f64)
+    tau_h, poses_h, tw_h, dtw_h = tau[0], poses[0], tw[0], dtw[0]
     pose_list = [se3_from_Rt(p) for p in poses_h] + [pose_tip_ee]
     twists = [twist_0] + [tw_h[i + 1] for i in range(nj)]
     dtwists = [dtwist_0] + [dtw_h[i + 1] for i in range(nj)]

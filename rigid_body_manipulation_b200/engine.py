@@ -160,6 +160,20 @@ class Model:
         _lib.check(rc, "rbm_rnea_full")
         return tau, poses, tw, dtw
 
+    def rnea_full_host(self, traj):
+        """Host-in / host-out version of `rnea_full` for small batches: traj (n, 3, nj) numpy -> numpy (tau, poses, twists, dtwists)."""
+        traj = np.ascontiguousarray(traj, dtype=np.float64)
+        if traj.ndim != 3 or traj.shape[1] != 3 or traj.shape[2] != self.nj:
+            raise ValueError(f"traj must have shape (n, 3, {self.nj})")
+        n, nj = traj.shape[0], self.nj
+        tau = np.empty((n, nj))
+        poses = np.empty((n, nj, 12))
+        tw = np.empty((n, nj + 1, 6))
+        dtw = np.empty((n, nj + 1, 6))
+        rc = self._lib.rbm_rnea_full_host_f64(self._h, _ptr(traj), _ptr(tau), _ptr(poses), _ptr(tw), _ptr(dtw), n)
+        _lib.check(rc, "rbm_rnea_full_host")
+        return tau, poses, tw, dtw
+
     # ---- planner-driven: trajectory generated in the kernel (no input traffic) -------------------------------------
     def rnea_planned(self, plan, n=None, step0=None, stride=1.0, dtype=torch.float64, want_traj=False, tau=None):
         """tau (nj, n) for steps step0 + s*stride of a planner.QuinticPlan (defaults: every planned step).
