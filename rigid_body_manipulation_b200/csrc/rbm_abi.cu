@@ -238,6 +238,20 @@ int rbm_model_create(int nj, const double* hposes_Rt, const double* simats, cons
     m->path = detect_path(nj, hposes_Rt, simats, uscrews, twist_0, dtwist_0, wrench_tip, pose_tip_Rt, &m->fp64);
   std::memcpy(m->fp64.senR, g + GP_SENR, 9 * sizeof(double));
   std::memcpy(m->fp64.sent, g + GP_SENT, 3 * sizeof(double));
+  {  // sensor pose with a diagonal rotation and no offset (snapped like the home rotations): Ad(T) acts component-wise
+    bool diag = m->path != PATH_GENERIC;
+    for (int r = 0; r < 3 && diag; ++r) {
+      for (int c = 0; c < 3; ++c) {
+        const double v = m->fp64.senR[3 * r + c];
+        if (r == c ? !(near(v, 1.0) || near(v, -1.0)) : !near(v, 0.0)) diag = false;
+      }
+      if (!near(m->fp64.sent[r], 0.0)) diag = false;
+    }
+    m->fp64.sen_diag = diag ? 1.0 : 0.0;
+    if (diag)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) m->fp64.senR[3 * r + c] = r == c ? (m->fp64.senR[3 * r + c] > 0 ? 1.0 : -1.0) : 0.0;
+  }
   convert_fast(m->fp64, &m->fp32);
 
   cudaError_t e = cudaSetDevice(device);

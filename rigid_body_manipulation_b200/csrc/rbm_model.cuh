@@ -49,6 +49,7 @@ struct FastParams {
   T tm[6][3];    // home translations (only read by descriptors that declare them non-zero)
   T senR[9];     // sensor pose rotation, row-major
   T sent[3];     // sensor pose translation
+  T sen_diag;    // 1 when senR is diagonal (+-1 entries) and sent == 0 (the reference's F/T site: Rz(180 deg)), else 0
 };
 
 enum KernelPath : int { PATH_GENERIC = 0, PATH_SEQ_ISO = 1, PATH_SEQ_RIGID = 2 };

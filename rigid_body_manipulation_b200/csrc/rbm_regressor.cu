@@ -180,7 +180,16 @@ __device__ __forceinline__ void gram_sample_fast(const FastParams<T>& P, const T
   T V[6], dV[6], Vs[6], dVs[6];
 #pragma unroll
   for (int k = 0; k < 3; ++k) { V[k] = r.v[k]; V[3 + k] = r.w[k]; dV[k] = r.a[k]; dV[3 + k] = r.l[k]; }
-  sensor_twists(P.senR, P.sent, V, dV, Vs, dVs);
+  if (P.sen_diag != T(0)) {  // warp-uniform: Ad(T) is a component-wise sign pattern
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const T d = P.senR[4 * k];
+      Vs[k] = d * V[k]; Vs[3 + k] = d * V[3 + k];
+      dVs[k] = d * dV[k]; dVs[3 + k] = d * dV[3 + k];
+    }
+  } else {
+    sensor_twists(P.senR, P.sent, V, dV, Vs, dVs);
+  }
   T top[3][4], bot[3][9];
   regressor_blocks(Vs, dVs, top, bot);
   gram_accumulate(acc, top, bot, fs);
