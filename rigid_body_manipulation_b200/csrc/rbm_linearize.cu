@@ -24,7 +24,7 @@ namespace rbm {
 
 constexpr int kLinBlock = 128;
 #ifndef RBM_LIN_MINB
-#define RBM_LIN_MINB 3
+#define RBM_LIN_MINB 2
 #endif
 
 // ---- inverse-dynamics evaluators ---------------------------------------------------------------------
@@ -46,6 +46,14 @@ struct FastEval {
   __device__ __forceinline__ void id(const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6], const T (&qdd)[6], T (&tau)[6]) const {
     FastResult<T> r;
     fast_rnea_core<T, D, true>(P, P.g, q, c, s, qd, qdd, r);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tau[k] = r.tau[k];
+  }
+  // velocity-product term alone, C(q, qd) = ID(q, qd, 0) without gravity.  tau = M qdd + C + g, so finite differences over qd
+  // at fixed (q, qdd) only need this part (and it is an exact quadratic form in qd: the centred difference has no truncation)
+  __device__ __forceinline__ void id_velocity(const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6], T (&tau)[6]) const {
+    FastResult<T> r;
+    fast_rnea_core<T, D, true, true, false, false>(P, P.g, q, c, s, qd, qd /* unused */, r);
 #pragma unroll
     for (int k = 0; k < 6; ++k) tau[k] = r.tau[k];
   }
@@ -72,6 +80,12 @@ struct GenericEval {
   __device__ __forceinline__ void id(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qd)[MAXJ], const T (&qdd)[MAXJ],
                                      T (&tau)[MAXJ]) const {
     generic_rnea<T, 0>(sp, sp, nj_, q, qd, qdd, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
+  }
+  __device__ __forceinline__ void id_velocity(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qd)[MAXJ], T (&tau)[MAXJ]) const {
+    T qdd0[MAXJ];
+#pragma unroll
+    for (int k = 0; k < MAXJ; ++k) qdd0[k] = T(0);
+    generic_rnea<T, 0>(sp, zero, nj_, q, qd, qdd0, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
   }
   __device__ __forceinline__ void id_inertia(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qdd)[MAXJ], T (&tau)[MAXJ]) const {
     T qd0[MAXJ];
@@ -127,6 +141,51 @@ __device__ __forceinline__ void chol_solve(const T (&L)[MAXJ][MAXJ], int n, T (&
   }
 }
 
+// M^-1 from the Cholesky factor, all unit right-hand sides at once: the nj substitutions are independent chains that the
+// compiler interleaves, instead of nj * 2 serial triangular sweeps (the serial sweeps were the kernel's main stall source).
+template <class T, int MAXJ>
+__device__ __forceinline__ void chol_inverse(const T (&L)[MAXJ][MAXJ], int n, T (&X)[MAXJ][MAXJ]) {
+  // forward: L Y = I  (Y lower triangular)
+#pragma unroll
+  for (int i = 0; i < MAXJ; ++i) {
+#pragma unroll
+    for (int c = 0; c < MAXJ; ++c) {
+      T v = (i == c) ? T(1) : T(0);
+      if (c <= i) {
+#pragma unroll
+        for (int k = 0; k < i; ++k)
+          if (k >= c) v -= L[i][k] * X[k][c];
+        X[i][c] = (i < n && c < n) ? v * L[i][i] : T(0);
+      } else {
+        X[i][c] = T(0);
+      }
+    }
+  }
+  // backward: L^T Z = Y
+#pragma unroll
+  for (int i = MAXJ - 1; i >= 0; --i) {
+#pragma unroll
+    for (int c = 0; c < MAXJ; ++c) {
+      T v = X[i][c];
+#pragma unroll
+      for (int k = i + 1; k < MAXJ; ++k)
+        if (k < n) v -= L[k][i] * X[k][c];
+      X[i][c] = (i < n && c < n) ? v * L[i][i] : T(0);
+    }
+  }
+}
+template <class T, int MAXJ>
+__device__ __forceinline__ void matvec(const T (&A)[MAXJ][MAXJ], int n, const T (&b)[MAXJ], T (&x)[MAXJ]) {
+#pragma unroll
+  for (int i = 0; i < MAXJ; ++i) {
+    T v = T(0);
+#pragma unroll
+    for (int k = 0; k < MAXJ; ++k)
+      if (k < n) v += A[i][k] * b[k];
+    x[i] = v;
+  }
+}
+
 // ---- the per-state algorithm ---------------------------------------------------------------------------
 template <class T, class E>
 __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict__ q_in, const T* __restrict__ qd_in, const T* __restrict__ u_in,
@@ -166,97 +225,147 @@ __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict
   T h[MJ], qdd[MJ];
   ev.id(q, c, sn, qd, zero, h);
   cholesky<T, MJ>(M, nj);
+  // fast path (nj fixed at compile time): explicit M^-1 once, then mat-vecs; generic path: one pair of triangular sweeps per
+  // right-hand side (a fully unrolled 16 x 16 inverse would not fit in registers)
+  constexpr bool kExplicitInverse = E::NJ > 0;
+  T Minv[kExplicitInverse ? MJ : 1][kExplicitInverse ? MJ : 1];
+  auto apply_inverse = [&](const T (&b)[MJ], T (&x)[MJ]) {
+    if constexpr (kExplicitInverse) {
+      matvec<T, MJ>(Minv, nj, b, x);
+    } else {
 #pragma unroll
-  for (int k = 0; k < MJ; ++k) qdd[k] = u[k] - h[k];
-  chol_solve<T, MJ>(M, nj, qdd);
+      for (int k = 0; k < MJ; ++k) x[k] = b[k];
+      chol_solve<T, MJ>(M, nj, x);
+    }
+  };
+  if constexpr (kExplicitInverse) chol_inverse<T, MJ>(M, nj, Minv);
+  {
+    T rhs[MJ];
+#pragma unroll
+    for (int k = 0; k < MJ; ++k) rhs[k] = u[k] - h[k];
+    apply_inverse(rhs, qdd);
+  }
   if (qdd_out) {
 #pragma unroll
     for (int k = 0; k < MJ; ++k)
       if (k < nj) qdd_out[k * ld + s] = qdd[k];
   }
   // B = [[dt^2 M^-1], [dt M^-1]]
-#pragma unroll 1
-  for (int j = 0; j < nj; ++j) {
-    T x[MJ];
-#pragma unroll
-    for (int k = 0; k < MJ; ++k) x[k] = (k == j) ? T(1) : T(0);
-    chol_solve<T, MJ>(M, nj, x);
+  if constexpr (kExplicitInverse) {
 #pragma unroll
     for (int r = 0; r < MJ; ++r) {
-      if (r < nj) {
-        B[((int64_t)r * nj + j) * ld + s] = dt * dt * x[r];
-        B[((int64_t)(nj + r) * nj + j) * ld + s] = dt * x[r];
+#pragma unroll
+      for (int j = 0; j < MJ; ++j) {
+        B[((int64_t)r * nj + j) * ld + s] = dt * dt * Minv[r][j];
+        B[((int64_t)(nj + r) * nj + j) * ld + s] = dt * Minv[r][j];
       }
     }
-  }
-  // reference value for forward differences: ID at the nominal point (== u up to round-off)
-  T tau0[MJ];
-  if (!centered) ev.id(q, c, sn, qd, qdd, tau0);
-  const T inv_step = centered ? T(1) / (T(2) * eps) : T(1) / eps;
-
-  // position columns, then velocity columns
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
+  } else {
 #pragma unroll 1
     for (int j = 0; j < nj; ++j) {
-      T xp[MJ], cp[MJ], sp_[MJ], tp[MJ], tm[MJ];
-      const T* src = pass == 0 ? q : qd;
-      const int col = pass * nj + j;
-      if (pass == 0 && !E::q_matters(j)) {  // d tau / d q_j is structurally zero: the column is that of the identity map
+      T e[MJ], x[MJ];
 #pragma unroll
-        for (int r = 0; r < MJ; ++r) {
-          if (r < nj) {
-            A[((int64_t)r * ns + col) * ld + s] = (r == j) ? T(1) : T(0);
-            A[((int64_t)(nj + r) * ns + col) * ld + s] = T(0);
-          }
-        }
-        continue;
-      }
-#pragma unroll
-      for (int k = 0; k < MJ; ++k) { xp[k] = src[k] + ((k == j) ? eps : T(0)); cp[k] = c[k]; sp_[k] = sn[k]; }
-      if (pass == 0 && E::is_hinge(j)) {
-        T qj = T(0), cj, sj;
-#pragma unroll
-        for (int k = 0; k < MJ; ++k) qj = (k == j) ? xp[k] : qj;
-        sincos_t(qj, &sj, &cj);
-#pragma unroll
-        for (int k = 0; k < MJ; ++k) { cp[k] = (k == j) ? cj : cp[k]; sp_[k] = (k == j) ? sj : sp_[k]; }
-      }
-      if (pass == 0) ev.id(xp, cp, sp_, qd, qdd, tp);
-      else ev.id(q, c, sn, xp, qdd, tp);
-      if (centered) {
-#pragma unroll
-        for (int k = 0; k < MJ; ++k) { xp[k] = src[k] - ((k == j) ? eps : T(0)); cp[k] = c[k]; sp_[k] = sn[k]; }
-        if (pass == 0 && E::is_hinge(j)) {
-          T qj = T(0), cj, sj;
-#pragma unroll
-          for (int k = 0; k < MJ; ++k) qj = (k == j) ? xp[k] : qj;
-          sincos_t(qj, &sj, &cj);
-#pragma unroll
-          for (int k = 0; k < MJ; ++k) { cp[k] = (k == j) ? cj : cp[k]; sp_[k] = (k == j) ? sj : sp_[k]; }
-        }
-        if (pass == 0) ev.id(xp, cp, sp_, qd, qdd, tm);
-        else ev.id(q, c, sn, xp, qdd, tm);
-      } else {
-#pragma unroll
-        for (int k = 0; k < MJ; ++k) tm[k] = tau0[k];
-      }
-      T x[MJ];
-#pragma unroll
-      for (int k = 0; k < MJ; ++k) x[k] = -(tp[k] - tm[k]) * inv_step;
-      chol_solve<T, MJ>(M, nj, x);   // column j of Q (pass 0) or V (pass 1)
+      for (int k = 0; k < MJ; ++k) e[k] = (k == j) ? T(1) : T(0);
+      apply_inverse(e, x);
 #pragma unroll
       for (int r = 0; r < MJ; ++r) {
         if (r < nj) {
-          const T delta = (r == j) ? T(1) : T(0);
-          T top, bot;
-          if (pass == 0) { top = delta + dt * dt * x[r]; bot = dt * x[r]; }
-          else { top = dt * (delta + dt * x[r]); bot = delta + dt * x[r]; }
-          A[((int64_t)r * ns + col) * ld + s] = top;
-          A[((int64_t)(nj + r) * ns + col) * ld + s] = bot;
+          B[((int64_t)r * nj + j) * ld + s] = dt * dt * x[r];
+          B[((int64_t)(nj + r) * nj + j) * ld + s] = dt * x[r];
         }
       }
     }
+  }
+  // reference values for forward differences: ID at the nominal point (== u up to round-off) and its velocity-product part
+  T tau0[MJ], vel0[MJ];
+  if (!centered) {
+    ev.id(q, c, sn, qd, qdd, tau0);
+    ev.id_velocity(q, c, sn, qd, vel0);
+  }
+  const T inv_step = centered ? T(1) / (T(2) * eps) : T(1) / eps;
+
+  // Finite-difference columns.  The +eps and -eps evaluations of a centred difference are issued back to back in one basic block
+  // so that their two independent dependency chains interleave (the kernel is latency-bound on FP64 chains at 8-12 warps/SM).
+  auto store_column = [&](int pass, int j, const T (&tp)[MJ], const T (&tm)[MJ]) {
+    T x[MJ], dtau[MJ];
+#pragma unroll
+    for (int k = 0; k < MJ; ++k) dtau[k] = -(tp[k] - tm[k]) * inv_step;
+    apply_inverse(dtau, x);  // column j of Q (pass 0) or V (pass 1)
+    const int col = pass * nj + j;
+#pragma unroll
+    for (int r = 0; r < MJ; ++r) {
+      if (r < nj) {
+        const T delta = (r == j) ? T(1) : T(0);
+        T top, bot;
+        if (pass == 0) { top = delta + dt * dt * x[r]; bot = dt * x[r]; }
+        else { top = dt * (delta + dt * x[r]); bot = delta + dt * x[r]; }
+        A[((int64_t)r * ns + col) * ld + s] = top;
+        A[((int64_t)(nj + r) * ns + col) * ld + s] = bot;
+      }
+    }
+  };
+
+  // ---- position columns ------------------------------------------------------------------------------------------------
+#pragma unroll 1
+  for (int j = 0; j < nj; ++j) {
+    if (!E::q_matters(j)) {  // d tau / d q_j is structurally zero: the column is that of the identity map
+#pragma unroll
+      for (int r = 0; r < MJ; ++r) {
+        if (r < nj) {
+          A[((int64_t)r * ns + j) * ld + s] = (r == j) ? T(1) : T(0);
+          A[((int64_t)(nj + r) * ns + j) * ld + s] = T(0);
+        }
+      }
+      continue;
+    }
+    T qp[MJ], qm[MJ], cp[MJ], sp_[MJ], cm[MJ], sm[MJ], tp[MJ], tm[MJ];
+#pragma unroll
+    for (int k = 0; k < MJ; ++k) {
+      const T d = (k == j) ? eps : T(0);
+      qp[k] = q[k] + d; qm[k] = q[k] - d;
+      cp[k] = cm[k] = c[k];
+      sp_[k] = sm[k] = sn[k];
+    }
+    if (E::is_hinge(j)) {  // only the perturbed joint needs new trigonometry; both signs as one group
+      T ang[2] = {T(0), T(0)}, sj[2], cj[2];
+#pragma unroll
+      for (int k = 0; k < MJ; ++k) { ang[0] = (k == j) ? qp[k] : ang[0]; ang[1] = (k == j) ? qm[k] : ang[1]; }
+      sincos_group<2, T>(ang, sj, cj);
+#pragma unroll
+      for (int k = 0; k < MJ; ++k) {
+        cp[k] = (k == j) ? cj[0] : cp[k]; sp_[k] = (k == j) ? sj[0] : sp_[k];
+        cm[k] = (k == j) ? cj[1] : cm[k]; sm[k] = (k == j) ? sj[1] : sm[k];
+      }
+    }
+    if (centered) {
+      ev.id(qp, cp, sp_, qd, qdd, tp);
+      ev.id(qm, cm, sm, qd, qdd, tm);
+    } else {
+      ev.id(qp, cp, sp_, qd, qdd, tp);
+#pragma unroll
+      for (int k = 0; k < MJ; ++k) tm[k] = tau0[k];
+    }
+    store_column(0, j, tp, tm);
+  }
+
+  // ---- velocity columns (velocity-product term only) ---------------------------------------------------------------------
+#pragma unroll 1
+  for (int j = 0; j < nj; ++j) {
+    T vp[MJ], vm[MJ], tp[MJ], tm[MJ];
+#pragma unroll
+    for (int k = 0; k < MJ; ++k) {
+      const T d = (k == j) ? eps : T(0);
+      vp[k] = qd[k] + d; vm[k] = qd[k] - d;
+    }
+    if (centered) {
+      ev.id_velocity(q, c, sn, vp, tp);
+      ev.id_velocity(q, c, sn, vm, tm);
+    } else {
+      ev.id_velocity(q, c, sn, vp, tp);
+#pragma unroll
+      for (int k = 0; k < MJ; ++k) tm[k] = vel0[k];
+    }
+    store_column(1, j, tp, tm);
   }
 }
 

@@ -9,8 +9,6 @@
 // non-zero entries of the two diagonal blocks in registers, blocks reduce with warp shuffles + shared
 // memory, and a second single-block kernel sums the per-block partials in a FIXED order (deterministic
 // result for a given grid).  HBM traffic per sample: q, qd, qdd, f = 24 scalars read, nothing written.
-#include <cstdlib>
-
 #include "rbm_async.cuh"
 #include "rbm_internal.h"
 #include "rbm_rnea.cuh"
@@ -301,17 +299,13 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* buf = reinterpret_cast<T*>(smem_raw);  // [S][kStreams][kGramBlock]
   __shared__ __align__(8) uint64_t full[S];
-  __shared__ int drained[S];  // warps that have copied their samples of the stage's current tile into registers
   __shared__ double red[kGramBlock / 32][kAcc];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t nfull = n / kGramBlock;  // tiles moved by bulk copies; a ragged tail tile is read directly
   for (int k = lane; k < kAcc; k += 32) red[warp][k] = 0.0;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], kGramBlock / 32);  // one arrive.expect_tx per warp (each brings its share of the 24 copies)
-      drained[s] = 0;
-    }
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], kGramBlock / 32);  // one arrive.expect_tx per warp (its share of the 24 copies)
     mbar_init_fence();
   }
   __syncthreads();

@@ -100,8 +100,8 @@ RBM_HD auto fwd_wrench(const FastParams<T>& P, const VV& v, const WW& w, const A
 }
 
 // One forward step (Eq. 8.50-8.52) plus the link's body wrench.
-template <class L, int I, class T, class QD, class VV, class WW, class AA, class LL>
-RBM_HD auto fwd_link(const FastParams<T>& P, T q, QD qd, T qdd, T c, T s, const VV& vp, const WW& wp, const AA& ap, const LL& lp) {
+template <class L, int I, class T, class QD, class QDD, class VV, class WW, class AA, class LL>
+RBM_HD auto fwd_link(const FastParams<T>& P, T q, QD qd, QDD qdd, T c, T s, const VV& vp, const WW& wp, const AA& ap, const LL& lp) {
   // translation of T_i = exp(-S q) * M_i
   auto tm = [&] {
     if constexpr (L::has_t) return ld3(P.tm[I]);
@@ -174,7 +174,7 @@ RBM_HD void fast_sincos(const T (&q)[6], T (&c)[6], T (&s)[6]) {
   }
 }
 
-template <class T, class D, bool WANT_TAU, bool VEL = true, bool GRAV = true>
+template <class T, class D, bool WANT_TAU, bool VEL = true, bool GRAV = true, bool ACC = true>
 RBM_HD void fast_rnea_core(const FastParams<T>& P, const T* g, const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6],
                            const T (&qdd)[6], FastResult<T>& out);
 
@@ -195,9 +195,10 @@ RBM_HD void fast_rnea(const FastParams<T>& P, const T (&q)[6], const T (&qd)[6],
 
 // The recursion itself; `g` is the linear part of the base acceleration (P.g, or zeros when the joint-space inertia
 // matrix is being extracted column by column).
-// VEL = false treats every joint velocity as a structural zero and GRAV = false the base acceleration (together: the
-// acceleration-only evaluation ID(q, 0, qdd) without gravity whose columns are the joint-space inertia matrix).
-template <class T, class D, bool WANT_TAU, bool VEL, bool GRAV>
+// VEL = false treats every joint velocity as a structural zero, GRAV = false the base acceleration and ACC = false every joint
+// acceleration: (VEL off, GRAV off) is the acceleration-only evaluation whose columns are the joint-space inertia matrix,
+// (ACC off, GRAV off) the velocity-product term C(q, qd) alone.
+template <class T, class D, bool WANT_TAU, bool VEL, bool GRAV, bool ACC>
 RBM_HD void fast_rnea_core(const FastParams<T>& P, const T* g, const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6],
                            const T (&qdd)[6], FastResult<T>& out) {
   // base: twist_0 = 0, dtwist_0 = [g; 0]  (core/simulate.py:149,154-155)
@@ -212,12 +213,16 @@ RBM_HD void fast_rnea_core(const FastParams<T>& P, const T* g, const T (&q)[6], 
     if constexpr (VEL) return qd[i];
     else return Z{};
   };
-  auto k0 = fwd_link<typename D::L0, 0>(P, q[0], vel(0), qdd[0], c[0], s[0], v0, w0, a0, l0);
-  auto k1 = fwd_link<typename D::L1, 1>(P, q[1], vel(1), qdd[1], c[1], s[1], k0.v, k0.w, k0.a, k0.l);
-  auto k2 = fwd_link<typename D::L2, 2>(P, q[2], vel(2), qdd[2], c[2], s[2], k1.v, k1.w, k1.a, k1.l);
-  auto k3 = fwd_link<typename D::L3, 3>(P, q[3], vel(3), qdd[3], c[3], s[3], k2.v, k2.w, k2.a, k2.l);
-  auto k4 = fwd_link<typename D::L4, 4>(P, q[4], vel(4), qdd[4], c[4], s[4], k3.v, k3.w, k3.a, k3.l);
-  auto k5 = fwd_link<typename D::L5, 5>(P, q[5], vel(5), qdd[5], c[5], s[5], k4.v, k4.w, k4.a, k4.l);
+  auto acc = [&](int i) {
+    if constexpr (ACC) return qdd[i];
+    else return Z{};
+  };
+  auto k0 = fwd_link<typename D::L0, 0>(P, q[0], vel(0), acc(0), c[0], s[0], v0, w0, a0, l0);
+  auto k1 = fwd_link<typename D::L1, 1>(P, q[1], vel(1), acc(1), c[1], s[1], k0.v, k0.w, k0.a, k0.l);
+  auto k2 = fwd_link<typename D::L2, 2>(P, q[2], vel(2), acc(2), c[2], s[2], k1.v, k1.w, k1.a, k1.l);
+  auto k3 = fwd_link<typename D::L3, 3>(P, q[3], vel(3), acc(3), c[3], s[3], k2.v, k2.w, k2.a, k2.l);
+  auto k4 = fwd_link<typename D::L4, 4>(P, q[4], vel(4), acc(4), c[4], s[4], k3.v, k3.w, k3.a, k3.l);
+  auto k5 = fwd_link<typename D::L5, 5>(P, q[5], vel(5), acc(5), c[5], s[5], k4.v, k4.w, k4.a, k4.l);
 
   out.v[0] = to_scalar<T>(k5.v.x); out.v[1] = to_scalar<T>(k5.v.y); out.v[2] = to_scalar<T>(k5.v.z);
   out.w[0] = to_scalar<T>(k5.w.x); out.w[1] = to_scalar<T>(k5.w.y); out.w[2] = to_scalar<T>(k5.w.z);
