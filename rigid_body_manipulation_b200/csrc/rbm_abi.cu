@@ -132,7 +132,8 @@ int rnea_host(const rbm_model* m, const T* traj_host, T* tau_host, int64_t n, in
   const int nj = m->nj;
   if (chunk <= 0) chunk = 1 << 18;
   if (chunk > n) chunk = n;
-  RBM_CUDA_TRY(cudaSetDevice(m->device));
+  DeviceGuard guard(m->device);
+  RBM_CUDA_TRY(guard.status());
   std::lock_guard<std::mutex> lock(m->pipe_mu);
   constexpr int kSlots = rbm_model::kPipeSlots;
   const size_t in_bytes = sizeof(T) * chunk * 3 * nj, out_bytes = sizeof(T) * chunk * nj;
@@ -254,7 +255,8 @@ int rbm_model_create(int nj, const double* hposes_Rt, const double* simats, cons
   }
   convert_fast(m->fp64, &m->fp32);
 
-  cudaError_t e = cudaSetDevice(device);
+  DeviceGuard guard(device);
+  cudaError_t e = guard.status();
   if (e == cudaSuccess) e = cudaMalloc(&m->d_gp64, np * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&m->d_gp32, np * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(m->d_gp64, m->gp64.data(), np * sizeof(double), cudaMemcpyHostToDevice);
@@ -289,7 +291,9 @@ int rbm_model_kernel_path(const rbm_model* m) { return m ? m->path : RBM_ERR_INV
 #define RBM_CHECK_BATCH(name)                                                         \
   if (!m) return invalid(name ": model is NULL");                                    \
   if (n < 0) return invalid(name ": n < 0");                                         \
-  if (n == 0) return RBM_OK;
+  if (n == 0) return RBM_OK;                                                         \
+  DeviceGuard rbm_guard_(m->device);                                                 \
+  RBM_CUDA_TRY(rbm_guard_.status());
 
 int rbm_rnea_f64(const rbm_model* m, const double* q, const double* qd, const double* qdd, double* tau, double* twist_last,
                  double* dtwist_last, int64_t n, int64_t ld, void* stream) {
@@ -365,7 +369,8 @@ int rbm_rnea_full_host_f64(const rbm_model* m, const double* traj_host, double* 
   const int nj = m->nj;
   const size_t n_in = (size_t)n * 3 * nj, n_tau = (size_t)n * nj, n_pose = (size_t)n * nj * 12, n_tw = (size_t)n * (nj + 1) * 6;
   const size_t total = n_in + n_tau + n_pose + 2 * n_tw;
-  RBM_CUDA_TRY(cudaSetDevice(m->device));
+  DeviceGuard guard(m->device);
+  RBM_CUDA_TRY(guard.status());
   std::lock_guard<std::mutex> lock(m->pipe_mu);
   if (total > m->full_doubles) {
     if (m->full_dev) cudaFree(m->full_dev);
@@ -427,6 +432,8 @@ int regressor_from_traj(const char* name, const rbm_model* m, const T* q, const 
   if (ld < n) return invalid(std::string(name) + ": ld < n");
   if ((Vs == nullptr) != (dVs == nullptr)) return invalid(std::string(name) + ": twist_sen and dtwist_sen go together");
   if ((phi == nullptr) != (F == nullptr)) return invalid(std::string(name) + ": phi and wrench go together");
+  DeviceGuard guard(m->device);
+  RBM_CUDA_TRY(guard.status());
   return launch_regressor_from_traj<T>(m, q, qd, qdd, Y, Vs, dVs, phi, F, n, ld, (cudaStream_t)stream);
 }
 template <class T>
@@ -438,6 +445,8 @@ int regressor_gram(const char* name, const rbm_model* m, const T* q, const T* qd
   if (n > 0 && (!q || !qd || !qdd || !f)) return invalid(std::string(name) + ": NULL batch pointer");
   if (ld < n) return invalid(std::string(name) + ": ld < n");
   if (ws_bytes < rbm_gram_workspace_bytes(m, n)) return invalid(std::string(name) + ": workspace too small (see rbm_gram_workspace_bytes)");
+  DeviceGuard guard(m->device);
+  RBM_CUDA_TRY(guard.status());
   return launch_regressor_gram<T>(m, q, qd, qdd, f, pack, static_cast<double*>(ws), n, ld, (cudaStream_t)stream);
 }
 }  // namespace

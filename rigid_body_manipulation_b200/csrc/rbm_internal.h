@@ -45,6 +45,30 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::rbm::cuda_fail(_e, #expr); \
   } while (0)
 
+// Makes `device` current for the scope and restores the caller's device afterwards (the library never leaves the calling
+// thread's current device changed; all model-bound entry points launch on the model's device).
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) prev_ = -1;
+    if (prev_ != device) {
+      status_ = cudaSetDevice(device);
+      switched_ = status_ == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched_ && prev_ >= 0) cudaSetDevice(prev_);
+  }
+  cudaError_t status() const { return status_; }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+
+ private:
+  int prev_ = -1;
+  bool switched_ = false;
+  cudaError_t status_ = cudaSuccess;
+};
+
 template <class T> struct ModelView;
 template <> struct ModelView<double> {
   static const double* generic(const rbm_model* m) { return m->d_gp64; }

@@ -92,7 +92,8 @@ int rbm_nccl_comm_create(const void* id128, int nranks, int rank, int device, vo
     return RBM_ERR_INVALID;
   }
   if (int rc = nccl_ready()) return rc;
-  RBM_CUDA_TRY(cudaSetDevice(device));
+  rbm::DeviceGuard guard(device);
+  RBM_CUDA_TRY(guard.status());
   ncclUniqueId id;
   std::memcpy(id.internal, id128, 128);
   ncclComm_t c = nullptr;

@@ -475,11 +475,12 @@ int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* 
     if (tma_ok) {
       grid = gram_grid(m, n, sizeof(T) == 4 ? 2 : 1);  // fp32: 119 registers, 96 KB of stages: two CTAs per SM
       constexpr size_t smem = (size_t)kGramStages * kStreams * kGramBlock * sizeof(T);
-      static bool attr_set = false;  // idempotent; set once per (T) instantiation and process
-      if (!attr_set) {
+      static bool attr_set[64] = {false};  // function attributes are per device; idempotent, so a benign race at worst
+      const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
+      if (!attr_set[dev]) {
         RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_tma<T, PATH_SEQ_ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_tma<T, PATH_SEQ_RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[dev] = true;
       }
       if (m->path == PATH_SEQ_ISO) k_regressor_gram_tma<T, PATH_SEQ_ISO><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
       else k_regressor_gram_tma<T, PATH_SEQ_RIGID><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
