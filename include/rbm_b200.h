@@ -180,6 +180,13 @@ RBM_API int rbm_allreduce_gram(void* comm, double* gram_pack, void* stream);
 RBM_API int rbm_linearize_f64(const rbm_model* m, const double* q, const double* qd, const double* u, double dt, double eps, int centered,
                       double* A, double* B, double* qdd, int64_t n, int64_t ld, void* stream);
 
+/* The transition itself (what rbm_linearize_f64 differentiates; MuJoCo's mj_forward + Euler integration for this plant,
+ * core/simulate.py:270):  qdd = M(q)^-1 (u - h(q, qd));  qd+ = qd + dt qdd;  q+ = q + dt qd+.
+ *   q, qd : [nj][ld];  u : [nj][ld] or NULL = zeros;  qdd : [nj][ld] or NULL;  q_next, qd_next : [nj][ld] or both NULL
+ * (q_next / qd_next may alias q / qd: every sample is read before it is written). */
+RBM_API int rbm_forward_dynamics_f64(const rbm_model* m, const double* q, const double* qd, const double* u, double dt, double* qdd, double* q_next,
+                             double* qd_next, int64_t n, int64_t ld, void* stream);
+
 /* ---- frame algebra helpers, batched (device pointers, AoS) ----------------------------------------------
  * transfer_simat (dynamics/dynamics.py:72-106): out[s] = Ad(T_s^-1)^T G_s Ad(T_s^-1); poses [n][12], simats [n][36]. */
 RBM_API int rbm_transfer_simat_f64(const double* poses_Rt, const double* simats, double* out, int64_t n, void* stream);

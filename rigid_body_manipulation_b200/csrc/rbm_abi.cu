@@ -484,6 +484,17 @@ int rbm_linearize_f64(const rbm_model* m, const double* q, const double* qd, con
   return launch_linearize<double>(m, q, qd, u, dt, eps, centered, A, B, qdd, n, ld, (cudaStream_t)stream);
 }
 
+int rbm_forward_dynamics_f64(const rbm_model* m, const double* q, const double* qd, const double* u, double dt, double* qdd, double* q_next,
+                             double* qd_next, int64_t n, int64_t ld, void* stream) {
+  RBM_CHECK_BATCH("rbm_forward_dynamics_f64")
+  if (!q || !qd) return invalid("rbm_forward_dynamics_f64: NULL batch pointer");
+  if (!qdd && !q_next) return invalid("rbm_forward_dynamics_f64: no output requested");
+  if ((q_next == nullptr) != (qd_next == nullptr)) return invalid("rbm_forward_dynamics_f64: q_next and qd_next go together");
+  if (q_next && !(dt > 0.0)) return invalid("rbm_forward_dynamics_f64: dt must be positive");
+  if (ld < n) return invalid("rbm_forward_dynamics_f64: ld < n");
+  return launch_forward_dynamics<double>(m, q, qd, u, dt, qdd, q_next, qd_next, n, ld, (cudaStream_t)stream);
+}
+
 // ---- frame algebra helpers ------------------------------------------------------------------------
 #define RBM_SIMPLE_CHECK(name, cond)                       \
   if (n < 0) return invalid(name ": n < 0");               \

@@ -369,6 +369,84 @@ __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict
   }
 }
 
+// ---- forward dynamics / one transition step (the map the linearisation differentiates) -------------------------------------
+//   qdd = M(q)^-1 (u - h(q, qd));   dt > 0:  qd+ = qd + dt qdd,  q+ = q + dt qd+   (semi-implicit Euler, MuJoCo's default)
+template <class T, class E>
+__device__ __forceinline__ void forward_dynamics_state(const E& ev, const T* __restrict__ q_in, const T* __restrict__ qd_in, const T* __restrict__ u_in,
+                                                       T dt, T* __restrict__ qdd_out, T* __restrict__ q_next, T* __restrict__ qd_next, int64_t s,
+                                                       int64_t ld) {
+  constexpr int MJ = E::MAXJ;
+  const int nj = ev.nj();
+  T q[MJ], qd[MJ], u[MJ], c[MJ], sn[MJ], zero[MJ];
+#pragma unroll
+  for (int k = 0; k < MJ; ++k) {
+    const bool on = k < nj;
+    q[k] = on ? __ldg(q_in + k * ld + s) : T(0);
+    qd[k] = on ? __ldg(qd_in + k * ld + s) : T(0);
+    u[k] = (on && u_in) ? __ldg(u_in + k * ld + s) : T(0);
+    zero[k] = T(0);
+    c[k] = T(1);
+    sn[k] = T(0);
+  }
+  ev.trig(q, c, sn);
+  T M[MJ][MJ];
+#pragma unroll 1
+  for (int j = 0; j < nj; ++j) {
+    T e[MJ], col[MJ];
+#pragma unroll
+    for (int k = 0; k < MJ; ++k) e[k] = (k == j) ? T(1) : T(0);
+    ev.id_inertia(q, c, sn, e, col);
+#pragma unroll
+    for (int r = 0; r < MJ; ++r)
+#pragma unroll
+      for (int k = 0; k < MJ; ++k)
+        if (k == j) M[r][k] = col[r];
+  }
+  T h[MJ], qdd[MJ];
+  ev.id(q, c, sn, qd, zero, h);
+  cholesky<T, MJ>(M, nj);
+#pragma unroll
+  for (int k = 0; k < MJ; ++k) qdd[k] = u[k] - h[k];
+  chol_solve<T, MJ>(M, nj, qdd);
+#pragma unroll
+  for (int k = 0; k < MJ; ++k) {
+    if (k < nj) {
+      if (qdd_out) qdd_out[k * ld + s] = qdd[k];
+      if (q_next) {
+        const T v = qd[k] + dt * qdd[k];
+        qd_next[k * ld + s] = v;
+        q_next[k * ld + s] = q[k] + dt * v;
+      }
+    }
+  }
+}
+
+template <class T, class D>
+__global__ void __launch_bounds__(kLinBlock) k_forward_dynamics_fast(const __grid_constant__ FastParams<T> P, const T* __restrict__ q, const T* __restrict__ qd,
+                                                                     const T* __restrict__ u, T dt, T* __restrict__ qdd, T* __restrict__ q_next,
+                                                                     T* __restrict__ qd_next, int64_t n, int64_t ld) {
+  const int64_t s = (int64_t)blockIdx.x * kLinBlock + threadIdx.x;
+  if (s >= n) return;
+  FastEval<T, D> ev{P};
+  forward_dynamics_state<T>(ev, q, qd, u, dt, qdd, q_next, qd_next, s, ld);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kLinBlock) k_forward_dynamics_generic(const T* __restrict__ gp, int nj, int nparams, const T* __restrict__ q,
+                                                                        const T* __restrict__ qd, const T* __restrict__ u, T dt, T* __restrict__ qdd,
+                                                                        T* __restrict__ q_next, T* __restrict__ qd_next, int64_t n, int64_t ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sp = reinterpret_cast<T*>(smem_raw);
+  T* zero = sp + nparams;
+  for (int i = threadIdx.x; i < nparams; i += blockDim.x) sp[i] = gp[i];
+  for (int i = threadIdx.x; i < 18; i += blockDim.x) zero[i] = T(0);
+  __syncthreads();
+  const int64_t s = (int64_t)blockIdx.x * kLinBlock + threadIdx.x;
+  if (s >= n) return;
+  GenericEval<T> ev{sp, zero, nj};
+  forward_dynamics_state<T>(ev, q, qd, u, dt, qdd, q_next, qd_next, s, ld);
+}
+
 template <class T, class D>
 __global__ void __launch_bounds__(kLinBlock, RBM_LIN_MINB) k_linearize_fast(const __grid_constant__ FastParams<T> P, const T* __restrict__ q, const T* __restrict__ qd,
                                                               const T* __restrict__ u, T dt, T eps, int centered, T* __restrict__ A, T* __restrict__ B,
@@ -413,6 +491,26 @@ int launch_linearize(const rbm_model* m, const T* q, const T* qd, const T* u, do
   return RBM_OK;
 }
 
+template <class T>
+int launch_forward_dynamics(const rbm_model* m, const T* q, const T* qd, const T* u, double dt, T* qdd, T* q_next, T* qd_next, int64_t n, int64_t ld,
+                            cudaStream_t st) {
+  if (n == 0) return RBM_OK;
+  const unsigned grid = (unsigned)((n + kLinBlock - 1) / kLinBlock);
+  if (m->path == PATH_SEQ_ISO) {
+    k_forward_dynamics_fast<T, SeqIso><<<grid, kLinBlock, 0, st>>>(ModelView<T>::fast(m), q, qd, u, (T)dt, qdd, q_next, qd_next, n, ld);
+  } else if (m->path == PATH_SEQ_RIGID) {
+    k_forward_dynamics_fast<T, SeqRigid><<<grid, kLinBlock, 0, st>>>(ModelView<T>::fast(m), q, qd, u, (T)dt, qdd, q_next, qd_next, n, ld);
+  } else {
+    const int np = generic_param_count(m->nj);
+    k_forward_dynamics_generic<T><<<grid, kLinBlock, sizeof(T) * (np + 18), st>>>(ModelView<T>::generic(m), m->nj, np, q, qd, u, (T)dt, qdd, q_next, qd_next,
+                                                                                n, ld);
+  }
+  RBM_CUDA_TRY(cudaGetLastError());
+  return RBM_OK;
+}
+
+template int launch_forward_dynamics<double>(const rbm_model*, const double*, const double*, const double*, double, double*, double*, double*, int64_t,
+                                             int64_t, cudaStream_t);
 template int launch_linearize<double>(const rbm_model*, const double*, const double*, const double*, double, double, int, double*, double*, double*, int64_t,
                                       int64_t, cudaStream_t);
 

@@ -287,6 +287,30 @@ class Model:
         return out + (qdd,) if want_qdd else out
 
 
+    def forward_dynamics(self, q, qd, u=None):
+        """qdd = M(q)^-1 (u - h(q, qd)) for CUDA tensors (nj, n) float64."""
+        self._check_dev(q, qd, u)
+        if q.dtype != torch.float64 or q.dim() != 2 or q.shape[0] != self.nj or qd.shape != q.shape:
+            raise ValueError(f"q, qd must be float64 with shape ({self.nj}, n)")
+        qdd = torch.empty_like(q)
+        with torch.cuda.device(self.device):
+            rc = self._lib.rbm_forward_dynamics_f64(self._h, _ptr(q), _ptr(qd), _ptr(u), 0.0, _ptr(qdd), None, None, q.shape[1], q.shape[1], self._stream())
+        _lib.check(rc, "rbm_forward_dynamics")
+        return qdd
+
+    def step(self, q, qd, u=None, dt=0.002, inplace=False):
+        """One semi-implicit Euler transition (q, qd) -> (q+, qd+) of the plant under joint forces u."""
+        self._check_dev(q, qd, u)
+        if q.dtype != torch.float64 or q.dim() != 2 or q.shape[0] != self.nj or qd.shape != q.shape:
+            raise ValueError(f"q, qd must be float64 with shape ({self.nj}, n)")
+        qn, qdn = (q, qd) if inplace else (torch.empty_like(q), torch.empty_like(qd))
+        with torch.cuda.device(self.device):
+            rc = self._lib.rbm_forward_dynamics_f64(self._h, _ptr(q), _ptr(qd), _ptr(u), float(dt), None, _ptr(qn), _ptr(qdn), q.shape[1], q.shape[1],
+                                                    self._stream())
+        _lib.check(rc, "rbm_forward_dynamics (step)")
+        return qn, qdn
+
+
 # ---- model-free batched helpers (device tensors in, device tensors out) ------------------------------------
 def _dev64(x, shape_tail):
     t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float64))

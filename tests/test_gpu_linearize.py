@@ -98,3 +98,83 @@ def test_one_million_states_runs_and_is_consistent():
     assert np.abs(A[idx] - Ar).max() < 5e-8
     assert np.abs(B[idx] - Br).max() < 5e-8
     assert np.isfinite(A).all() and np.isfinite(B).all()
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_forward_dynamics_and_step_match_the_oracle_and_the_linearisation(force_generic):
+    """rbm_forward_dynamics_f64: qdd and the semi-implicit Euler transition against the CPU restatement; and the transition's own
+    finite differences (GPU step, eps 1e-6) against the A, B the linearisation kernel returns."""
+    g = load_golden("ref_inverse_uniform_gearbox.npz")
+    m = model_from_golden(g, force_generic=force_generic)
+    c = consts_of(g)
+    n, dt = 64, 0.002
+    tr = sample_states(np.random.default_rng(21), n)
+    q, qd = tr[:, 0], tr[:, 1]
+    u = np.random.default_rng(22).standard_normal((n, 6)) * np.array([100, 100, 400, 1, 1, 1.0])
+    to = lambda a: torch.as_tensor(np.ascontiguousarray(a.T), device="cuda")
+    qdd = m.forward_dynamics(to(q), to(qd), to(u)).t().cpu().numpy()
+    ref = lo.forward_dynamics(c, q, qd, u)
+    assert np.abs(qdd - ref).max() < 1e-9 * np.abs(ref).max()
+    qn, qdn = m.step(to(q), to(qd), to(u), dt=dt)
+    y = lo.step(c, q, qd, u, dt)
+    assert np.abs(np.concatenate([qn.t().cpu().numpy(), qdn.t().cpu().numpy()], 1) - y).max() < 1e-11 * np.abs(y).max()
+    # in-place stepping (aliasing allowed) gives the same bits
+    qi, qdi = to(q), to(qd)
+    m.step(qi, qdi, to(u), dt=dt, inplace=True)
+    assert torch.equal(qi, qn) and torch.equal(qdi, qdn)
+    # finite differences of the GPU transition == the linearisation kernel's A, B
+    A, B, _ = run(m, q, qd, u, dt=dt, eps=1e-6, centered=True)
+    eps = 1e-6
+    x0 = np.concatenate([q, qd], 1)
+    for i in range(12):
+        d = np.zeros(12)
+        d[i] = eps
+        xp, xm = x0 + d, x0 - d
+        yp = torch.cat(m.step(to(xp[:, :6]), to(xp[:, 6:]), to(u), dt=dt)).t().cpu().numpy()
+        ym = torch.cat(m.step(to(xm[:, :6]), to(xm[:, 6:]), to(u), dt=dt)).t().cpu().numpy()
+        assert np.abs((yp - ym) / (2 * eps) - A[:, :, i]).max() < 5e-8
+    for k in range(6):
+        d = np.zeros(6)
+        d[k] = eps
+        yp = torch.cat(m.step(to(q), to(qd), to(u + d), dt=dt)).t().cpu().numpy()
+        ym = torch.cat(m.step(to(q), to(qd), to(u - d), dt=dt)).t().cpu().numpy()
+        assert np.abs((yp - ym) / (2 * eps) - B[:, :, k]).max() < 5e-8
+
+
+def test_closed_loop_tracking_with_lqr():
+    """End-to-end consistency of the pieces the reference's control loop is made of (core/simulate.py:185-270,
+    controllers/lqr.py:38-51), batched over 256 perturbed rollouts: planner -> feed-forward tau (RNEA) -> LQR gain from the
+    kernel's A, B (DARE on the host) -> transition kernel.  With the exact model the feed-forward alone tracks the plan up to the
+    integrator's O(dt) error, and the feedback pulls perturbed starts back; without feedback they are not pulled back.
+    (The stabilising sign u = tau_ff + K (x_target - x) is used; the reference's own loop subtracts, simulate.py:268.)"""
+    from scipy import linalg
+
+    from rigid_body_manipulation_b200.planner import traj_5th_spline
+
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    dt, n_steps, nroll = 0.002, 400, 256
+    plan = traj_5th_spline([0.2, 0.4, 0.6, np.pi, 0.3 * np.pi, 1.5 * np.pi], g["key_qpos"], dt, n_steps)  # uniform.yaml-like motion
+    tau_ff, traj = m.rnea_planned(plan, want_traj=True)  # (6, T), (3, 6, T)
+    A, B, _ = run(m, g["key_qpos"][None], np.zeros((1, 6)), None, dt=dt, eps=1e-6)
+    R = np.diag([1.0] * 6)
+    Q = np.diag([1e6] * 6 + [1e3] * 6)  # stiff enough to converge within the 0.8 s motion (prototyped on the CPU oracle)
+    P = linalg.solve_discrete_are(A[0], B[0], Q, R)
+    K = torch.as_tensor(linalg.solve(R + B[0].T @ P @ B[0], B[0].T @ P @ A[0]), device="cuda")  # (6, 12)
+    rng = np.random.default_rng(0)
+    x0 = np.concatenate([g["key_qpos"], np.zeros(6)])[:, None] + rng.standard_normal((12, nroll)) * np.array([[0.02]] * 6 + [[0.05]] * 6)
+
+    def rollout(gain):
+        q = torch.as_tensor(x0[:6].copy(), device="cuda")
+        qd = torch.as_tensor(x0[6:].copy(), device="cuda")
+        for k in range(n_steps):
+            xt = torch.cat([traj[0, :, k], traj[1, :, k]])[:, None]
+            u = tau_ff[:, k : k + 1] + gain * (K @ (xt - torch.cat([q, qd])))
+            m.step(q, qd, u.contiguous(), dt=dt, inplace=True)
+        xt = torch.cat([traj[0, :, -1], traj[1, :, -1]])[:, None]
+        return (torch.cat([q, qd]) - xt).abs().amax(dim=0).cpu().numpy()
+
+    err_fb, err_open = rollout(1.0), rollout(0.0)
+    assert np.isfinite(err_fb).all()
+    assert err_fb.max() < 0.05, err_fb.max()          # pulled back onto the plan (what remains is the integrator's O(dt) lag)
+    assert np.median(err_open) > 5 * np.median(err_fb)  # without feedback the initial offsets persist / grow
