@@ -168,6 +168,8 @@ RBM_API int rbm_nccl_unique_id(void* id128);
 RBM_API int rbm_nccl_comm_create(const void* id128, int nranks, int rank, int device, void** comm);
 RBM_API int rbm_nccl_comm_destroy(void* comm);
 RBM_API int rbm_allreduce_gram(void* comm, double* gram_pack, void* stream);
+/* grouped form: `count` consecutive packs (one per object), one collective */
+RBM_API int rbm_allreduce_gram_n(void* comm, double* gram_packs, int64_t count, void* stream);
 
 /* ---- LQR linearisation ------------------------------------------------------------------------------------
  * Replaces dynamics.StateSpace.update_matrices (dynamics/dynamics.py:41-46 -> mjd_transitionFD, consumed by

@@ -71,6 +71,7 @@ SIGNATURES = {
     "rbm_nccl_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "rbm_nccl_comm_destroy": (C.c_int, [_vp]),
     "rbm_allreduce_gram": (C.c_int, [_vp, _vp, _vp]),
+    "rbm_allreduce_gram_n": (C.c_int, [_vp, _vp, _i64, _vp]),
     "rbm_linearize_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp, _i64, _i64, _vp]),
     "rbm_forward_dynamics_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _i64, _i64, _vp]),
     "rbm_transfer_simat_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),

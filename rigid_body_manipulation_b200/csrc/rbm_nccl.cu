@@ -110,14 +110,17 @@ int rbm_nccl_comm_destroy(void* comm) {
   return r == 0 ? RBM_OK : nccl_fail("ncclCommDestroy", r);
 }
 
-int rbm_allreduce_gram(void* comm, double* gram_pack, void* stream) {
-  if (!comm || !gram_pack) {
-    rbm::set_error("rbm_allreduce_gram: NULL communicator or pack");
+int rbm_allreduce_gram_n(void* comm, double* gram_packs, int64_t count, void* stream) {
+  if (!comm || !gram_packs || count < 1) {
+    rbm::set_error("rbm_allreduce_gram: NULL communicator / pack or count < 1");
     return RBM_ERR_INVALID;
   }
   if (int rc = nccl_ready()) return rc;
-  ncclResult_t r = api().AllReduce(gram_pack, gram_pack, 112, kNcclDouble, kNcclSum, static_cast<ncclComm_t>(comm), static_cast<cudaStream_t>(stream));
+  ncclResult_t r = api().AllReduce(gram_packs, gram_packs, (size_t)count * 112, kNcclDouble, kNcclSum, static_cast<ncclComm_t>(comm),
+                                   static_cast<cudaStream_t>(stream));
   return r == 0 ? RBM_OK : nccl_fail("ncclAllReduce", r);
 }
+
+int rbm_allreduce_gram(void* comm, double* gram_pack, void* stream) { return rbm_allreduce_gram_n(comm, gram_pack, 1, stream); }
 
 }  // extern "C"

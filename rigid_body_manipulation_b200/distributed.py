@@ -23,9 +23,10 @@ def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def allreduce_gram(pack: torch.Tensor, group=None) -> torch.Tensor:
-    """In-place sum of the [Y^T Y | Y^T f | f^T f | n] pack over all ranks (no-op without an initialised group)."""
-    if pack.numel() != 112 or pack.dtype != torch.float64:
-        raise ValueError("pack must be 112 float64 values")
+    """In-place sum of the [Y^T Y | Y^T f | f^T f | n] pack over all ranks (no-op without an initialised group).
+    A (k, 112) tensor holds one pack per object and is reduced in ONE collective (grouped all-reduce)."""
+    if pack.dim() not in (1, 2) or pack.shape[-1] != 112 or pack.dtype != torch.float64 or not pack.is_contiguous():
+        raise ValueError("pack must be a contiguous float64 tensor of shape (112,) or (k, 112)")
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
     return pack
@@ -60,10 +61,11 @@ class NcclGramReducer:
     def __call__(self, pack: torch.Tensor) -> torch.Tensor:
         import ctypes as C
 
-        if pack.numel() != 112 or pack.dtype != torch.float64 or not pack.is_cuda or not pack.is_contiguous():
-            raise ValueError("pack must be a contiguous CUDA tensor of 112 float64 values")
+        if pack.dim() not in (1, 2) or pack.shape[-1] != 112 or pack.dtype != torch.float64 or not pack.is_cuda or not pack.is_contiguous():
+            raise ValueError("pack must be a contiguous CUDA float64 tensor of shape (112,) or (k, 112)")
         stream = C.c_void_p(torch.cuda.current_stream(pack.device).cuda_stream)
-        self._check(self._lib.rbm_allreduce_gram(self._comm, C.c_void_p(pack.data_ptr()), stream), "rbm_allreduce_gram")
+        count = pack.numel() // 112
+        self._check(self._lib.rbm_allreduce_gram_n(self._comm, C.c_void_p(pack.data_ptr()), count, stream), "rbm_allreduce_gram_n")
         return pack
 
     def close(self):

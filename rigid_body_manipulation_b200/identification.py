@@ -53,6 +53,14 @@ def solve(pack, rcond: float = 1e-13) -> Identification:
     return Identification(phi=phi, n_samples=n, residual_ss=rss, f_ss=ff, rms_residual=float(np.sqrt(rss / max(6.0 * n, 1.0))), cond=cond, rank=int(keep.sum()))
 
 
+def solve_many(packs, rcond: float = 1e-13) -> list:
+    """One identification per row of a (k, 112) stack of packs (e.g. one object per row after a grouped all-reduce)."""
+    p = np.asarray(packs.detach().cpu().numpy() if hasattr(packs, "detach") else packs, dtype=np.float64)
+    if p.ndim != 2 or p.shape[1] != 112:
+        raise ValueError("packs must have shape (k, 112)")
+    return [solve(row, rcond) for row in p]
+
+
 def score(estimate, gt_params, aabb_scale: float) -> float:
     """The reference's normalised squared error (main.py:21-38): mass / first moments / inertias made dimensionless with
     m, m*L, m*L^2 (L = aabb_scale), averaged over the 10 parameters."""

@@ -186,3 +186,37 @@ def test_config1_identification_pipeline():
     # noise-free: exact recovery of the CAD parameters expressed in the sensor frame
     clean = identification.solve(m.regressor_gram(q, qd, qdd, torch.as_tensor(f_clean, device="cuda").t().contiguous()))
     assert np.abs(clean.phi - phi_true).max() < 1e-6 * max(1.0, clean.cond * 1e-6)
+
+
+def test_per_object_grams_for_all_packaged_targets():
+    """SURVEY.md 8(f) rank 2 / north star "10x10 per object": one model per target object (all 23 CAD rows), one Gram pack per
+    object stacked as (23, 112), identified in one go; every object's sensor-frame parameters are recovered from noise-free data."""
+    from rigid_body_manipulation_b200 import model as rbm_model
+    from rigid_body_manipulation_b200.engine import Model
+
+    names = sorted(rbm_model.packaged_targets())
+    assert len(names) == 23
+    n = 20_000
+    q, qd, qdd = soa(sample_states(np.random.default_rng(77), n))
+    packs = torch.empty((len(names), 112), dtype=torch.float64, device="cuda")
+    truths = []
+    for k, name in enumerate(names):
+        c = rbm_model.load_packaged("sequential", name)
+        m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, pose_sen_llj=c.pose_sen_Rt)
+        assert m.kernel_path == "seq_iso"
+        # the wrench the object loads the sensor with: its own inertia (the reference's diag-inertia recipe) seen from the sensor frame
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = c.pose_sen_Rt[:9].reshape(3, 3), c.pose_sen_Rt[9:]
+        G = rbm_model.move_inertia(T, c.simat_object_llj)
+        phi = np.array([G[0, 0], G[5, 1], G[3, 2], G[4, 0], G[3, 3], G[4, 4], G[5, 5], G[3, 4], G[4, 5], G[5, 3]])
+        truths.append(phi)
+        f = m.regressor_from_traj(q, qd, qdd, want_rows=False, phi=phi)["wrench"]
+        m.regressor_gram(q, qd, qdd, f, pack=packs[k])
+    from rigid_body_manipulation_b200 import distributed
+
+    distributed.allreduce_gram(packs)  # grouped form; a no-op on one rank
+    res = identification.solve_many(packs)
+    for name, r, phi in zip(names, res, truths):
+        assert r.rank == 10 and r.n_samples == n, name
+        scale = np.array([phi[0]] * 4 + [max(np.abs(phi[4:]).max(), 1e-12)] * 6)
+        assert (np.abs(r.phi - phi) / scale).max() < 1e-7, (name, r.phi, phi)
