@@ -5,6 +5,7 @@
 // re-read: HBM traffic == algorithmic traffic == 24 * sizeof(T) bytes per sample.
 #include <cstdlib>
 
+#include "rbm_async.cuh"
 #include "rbm_internal.h"
 #include "rbm_rnea.cuh"
 
@@ -147,6 +148,79 @@ __global__ void __launch_bounds__(kBlock) k_rnea_fast_aos(const __grid_constant_
   for (int i = threadIdx.x; i < cnt * 6; i += kBlock) dst[i] = tile[i];
 }
 
+// TMA variant of the AoS kernel (fast paths): a tile of kBlock samples is ONE contiguous span in both arrays (18 KB in, 6 KB out in
+// fp64), so each tile is one bulk load and one bulk store.  Persistent CTAs keep kAosStages loads in flight; results are staged
+// in a double-buffered shared tile and leave through the async proxy while the next tile is being computed.
+constexpr int kAosStages = 3;
+
+template <class T, class D>
+__global__ void __launch_bounds__(kBlock) k_rnea_fast_aos_tma(const __grid_constant__ FastParams<T> P, const T* __restrict__ traj, T* __restrict__ tau,
+                                                              int64_t n) {
+  constexpr int S = kAosStages;
+  constexpr uint32_t kInBytes = kBlock * 18 * sizeof(T), kOutBytes = kBlock * 6 * sizeof(T);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* in_buf = reinterpret_cast<T*>(smem_raw);                      // [S][kBlock * 18]
+  T* out_buf = in_buf + (size_t)S * kBlock * 18;                   // [2][kBlock * 6]
+  __shared__ __align__(8) uint64_t full[S];
+  const int tid = threadIdx.x;
+  const int64_t nfull = n / kBlock;  // full tiles go through the TMA pipeline; the ragged tail is handled with plain accesses
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t it) {
+    const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= nfull) return;
+    const int st = (int)(it % S);
+    mbar_arrive_expect_tx(&full[st], kInBytes);
+    bulk_copy_g2s(in_buf + (size_t)st * kBlock * 18, traj + tile * (kBlock * 18), kInBytes, &full[st]);
+  };
+  if (tid == 0) {
+    for (int it = 0; it < S; ++it) issue(it);
+  }
+  for (int64_t it = 0;; ++it) {
+    const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= nfull) break;
+    const int st = (int)(it % S);
+    mbar_wait(&full[st], (uint32_t)((it / S) & 1));
+    const T* my = in_buf + (size_t)st * kBlock * 18 + tid * 18;
+    T rq[6], rqd[6], rqdd[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { rq[j] = my[j]; rqd[j] = my[6 + j]; rqdd[j] = my[12 + j]; }
+    if (tid == 0) bulk_wait_group_read<1>();  // the store that read out_buf[it & 1] two tiles ago has drained it
+    __syncthreads();                          // inputs are in registers everywhere; out_buf[it & 1] is free
+    if (tid == 0) issue(it + S);
+    FastResult<T> r;
+    fast_rnea<T, D, true>(P, rq, rqd, rqdd, r);
+    T* out = out_buf + (size_t)(it & 1) * kBlock * 6;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) out[tid * 6 + j] = r.tau[j];
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_copy_s2g(tau + tile * (kBlock * 6), out, kOutBytes);
+      bulk_commit_group();
+    }
+  }
+  if (tid == 0) bulk_wait_group<0>();  // all stores complete before the CTA (and its shared memory) goes away
+  // ragged tail: at most kBlock - 1 samples, owned by the CTA that would have received tile `nfull`
+  if ((nfull % gridDim.x) == blockIdx.x) {
+    const int64_t s = nfull * kBlock + tid;
+    if (s < n) {
+      const T* my = traj + s * 18;
+      T rq[6], rqd[6], rqdd[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { rq[j] = __ldg(my + j); rqd[j] = __ldg(my + 6 + j); rqdd[j] = __ldg(my + 12 + j); }
+      FastResult<T> r;
+      fast_rnea<T, D, true>(P, rq, rqd, rqdd, r);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) tau[s * 6 + j] = r.tau[j];
+    }
+  }
+}
+
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_rnea_generic_aos(const T* __restrict__ gp, int nj, int nparams, const T* __restrict__ traj,
                                                              T* __restrict__ tau, T* __restrict__ poses, T* __restrict__ twists,
@@ -274,7 +348,23 @@ template <class T>
 int launch_rnea_aos(const rbm_model* m, const T* traj, T* tau, int64_t n, cudaStream_t st) {
   if (n == 0) return RBM_OK;
   const unsigned grid = grid_for(n);
-  if (m->path == PATH_SEQ_ISO) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(traj) | reinterpret_cast<uintptr_t>(tau)) & 15u) == 0;
+  if (m->path != PATH_GENERIC && aligned && !m->no_tma && n >= kBlock) {
+    constexpr size_t smem = ((size_t)kAosStages * 18 + 2 * 6) * kBlock * sizeof(T);
+    static bool attr_set[64] = {false};
+    const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
+    if (!attr_set[dev]) {
+      RBM_CUDA_TRY(cudaFuncSetAttribute(k_rnea_fast_aos_tma<T, SeqIso>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RBM_CUDA_TRY(cudaFuncSetAttribute(k_rnea_fast_aos_tma<T, SeqRigid>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set[dev] = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+    const int64_t tiles = n / kBlock;
+    const unsigned pgrid = (unsigned)(tiles < (int64_t)sms * 3 ? tiles : (int64_t)sms * 3);  // ~68 KB of stages per CTA: three CTAs per SM
+    if (m->path == PATH_SEQ_ISO) k_rnea_fast_aos_tma<T, SeqIso><<<pgrid, kBlock, smem, st>>>(ModelView<T>::fast(m), traj, tau, n);
+    else k_rnea_fast_aos_tma<T, SeqRigid><<<pgrid, kBlock, smem, st>>>(ModelView<T>::fast(m), traj, tau, n);
+  } else if (m->path == PATH_SEQ_ISO) {
     k_rnea_fast_aos<T, SeqIso><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), traj, tau, n);
   } else if (m->path == PATH_SEQ_RIGID) {
     k_rnea_fast_aos<T, SeqRigid><<<grid, kBlock, 0, st>>>(ModelView<T>::fast(m), traj, tau, n);
