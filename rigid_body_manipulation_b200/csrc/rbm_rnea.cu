@@ -77,6 +77,12 @@ __global__ void __launch_bounds__(kBlock) k_rnea_fast_soa(const __grid_constant_
   }
 }
 
+// Experiment log (round 1, B200): staging the SoA inputs through the TMA unit does NOT pay for this kernel.  fp32, G samples/s
+// at 2^20 / 1e7 / 1e8 samples: plain coalesced loads (this kernel) 57.5 / 62.6 / 64.3; 18 one-row bulk copies per 256-sample tile
+// 45.4 / 53.0 / 54.2 (the TMA unit is per-copy bound at 1 KB); three 2-D tensor-map copies (box 256 x 6) per tile 51.0 / 61.4 / 63.7;
+// the same plus a tensor-map store of tau 51.5 / 59.9 / 62.0.  The AoS kernel below is different: there a tile is ONE contiguous
+// span, one bulk load and one bulk store, and TMA wins clearly.
+
 // ---------------------------------------------------------------------------------------------
 // generic path, SoA.  Parameters are staged once per block into shared memory.
 // ---------------------------------------------------------------------------------------------

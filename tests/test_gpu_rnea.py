@@ -277,3 +277,25 @@ def test_maximum_size_property_fp32():
     t0 = m.rnea(q, qd, qdd)
     lin = (t2 - t1).sub_(t1).add_(t0).abs_().amax().item()
     assert lin < 2e-4 * t1.abs().amax().item()
+
+
+@pytest.mark.parametrize("n", [1024, 4096 + 77, 300_004, 1 << 20])
+@pytest.mark.parametrize("no_tma", [False, True])
+def test_fp32_soa_sizes_and_flags(n, no_tma):
+    """fp32 SoA batches of several sizes / alignments (with and without RBM_FLAG_NO_TMA, which only affects the AoS and Gram
+    kernels) against the fp64 C oracle at 1e-4; and the AoS entry point on the same data (TMA in / out when aligned)."""
+    from oracle import build_c
+
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g, no_tma=no_tma)
+    traj = sample_states(np.random.default_rng(n), n)
+    ref = build_c.inverse_batched_c(traj, g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"])
+    q, qd, qdd = soa(traj, torch.float32)
+    tau = m.rnea(q, qd, qdd)
+    assert rel_err(tau.t().cpu().numpy(), ref).max() < TOL32
+    tau_tw, V, dV = m.rnea(q, qd, qdd, want_twists=True)
+    assert torch.equal(tau, tau_tw)
+    tau_aos = m.rnea_aos(torch.as_tensor(traj, dtype=torch.float32, device="cuda"))
+    assert rel_err(tau_aos.cpu().numpy(), ref).max() < TOL32
+    tau_aos64 = m.rnea_aos(torch.as_tensor(traj, device="cuda"))
+    assert rel_err(tau_aos64.cpu().numpy(), ref).max() < TOL64
