@@ -77,6 +77,64 @@ __global__ void __launch_bounds__(kBlock) k_rnea_fast_soa(const __grid_constant_
   }
 }
 
+// fp32 variant with two consecutive samples per thread and 8-byte vector accesses: the fp32 kernel is issue-bound, and this
+// halves the load / store / address instructions per sample while giving the scheduler two independent chains to interleave.
+template <class D, bool OUT_TWIST>
+__global__ void __launch_bounds__(kBlock) k_rnea_fast_soa_f32x2(const __grid_constant__ FastParams<float> P, const float* __restrict__ q,
+                                                                const float* __restrict__ qd, const float* __restrict__ qdd, float* __restrict__ tau,
+                                                                float* __restrict__ Vout, float* __restrict__ dVout, int64_t n, int64_t ld) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();
+  const int64_t s = 2 * ((int64_t)blockIdx.x * kBlock + threadIdx.x);
+  if (s >= n) return;
+  float a_q[6], a_qd[6], a_qdd[6], b_q[6], b_qd[6], b_qdd[6];
+  const bool pair = s + 1 < n;
+  if (pair) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float2 v0 = __ldg(reinterpret_cast<const float2*>(q + j * ld + s));
+      const float2 v1 = __ldg(reinterpret_cast<const float2*>(qd + j * ld + s));
+      const float2 v2 = __ldg(reinterpret_cast<const float2*>(qdd + j * ld + s));
+      a_q[j] = v0.x; b_q[j] = v0.y; a_qd[j] = v1.x; b_qd[j] = v1.y; a_qdd[j] = v2.x; b_qdd[j] = v2.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      a_q[j] = b_q[j] = __ldg(q + j * ld + s);
+      a_qd[j] = b_qd[j] = __ldg(qd + j * ld + s);
+      a_qdd[j] = b_qdd[j] = __ldg(qdd + j * ld + s);
+    }
+  }
+  FastResult<float> ra, rb;
+  fast_rnea<float, D, true>(P, a_q, a_qd, a_qdd, ra);
+  fast_rnea<float, D, true>(P, b_q, b_qd, b_qdd, rb);
+  if (pair) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) *reinterpret_cast<float2*>(tau + j * ld + s) = make_float2(ra.tau[j], rb.tau[j]);
+    if constexpr (OUT_TWIST) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        *reinterpret_cast<float2*>(Vout + j * ld + s) = make_float2(ra.v[j], rb.v[j]);
+        *reinterpret_cast<float2*>(Vout + (j + 3) * ld + s) = make_float2(ra.w[j], rb.w[j]);
+        *reinterpret_cast<float2*>(dVout + j * ld + s) = make_float2(ra.a[j], rb.a[j]);
+        *reinterpret_cast<float2*>(dVout + (j + 3) * ld + s) = make_float2(ra.l[j], rb.l[j]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) tau[j * ld + s] = ra.tau[j];
+    if constexpr (OUT_TWIST) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        Vout[j * ld + s] = ra.v[j];
+        Vout[(j + 3) * ld + s] = ra.w[j];
+        dVout[j * ld + s] = ra.a[j];
+        dVout[(j + 3) * ld + s] = ra.l[j];
+      }
+    }
+  }
+}
+
 // Experiment log (round 1, B200): staging the SoA inputs through the TMA unit does NOT pay for this kernel.  fp32, G samples/s
 // at 2^20 / 1e7 / 1e8 samples: plain coalesced loads (this kernel) 57.5 / 62.6 / 64.3; 18 one-row bulk copies per 256-sample tile
 // 45.4 / 53.0 / 54.2 (the TMA unit is per-copy bound at 1 KB); three 2-D tensor-map copies (box 256 x 6) per tile 51.0 / 61.4 / 63.7;
@@ -334,6 +392,22 @@ int launch_rnea_soa(const rbm_model* m, const T* q, const T* qd, const T* qdd, T
   if (n == 0) return RBM_OK;
   const unsigned grid = grid_for(n);
   const bool tw = (V != nullptr);
+  if constexpr (sizeof(T) == 4) {
+    // two samples per thread with float2 accesses when every row is 8-byte aligned
+    auto al8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
+    if (m->path != PATH_GENERIC && (ld % 2) == 0 && al8(q) && al8(qd) && al8(qdd) && al8(tau) && (!tw || (al8(V) && al8(dV)))) {
+      const unsigned g2 = grid_for((n + 1) / 2);
+      const FastParams<float>& P = ModelView<float>::fast(m);
+      if (m->path == PATH_SEQ_ISO) {
+        if (tw) RBM_CUDA_TRY(launch_pdl(k_rnea_fast_soa_f32x2<SeqIso, true>, g2, kBlock, 0, st, P, q, qd, qdd, tau, V, dV, n, ld));
+        else RBM_CUDA_TRY(launch_pdl(k_rnea_fast_soa_f32x2<SeqIso, false>, g2, kBlock, 0, st, P, q, qd, qdd, tau, V, dV, n, ld));
+      } else {
+        if (tw) RBM_CUDA_TRY(launch_pdl(k_rnea_fast_soa_f32x2<SeqRigid, true>, g2, kBlock, 0, st, P, q, qd, qdd, tau, V, dV, n, ld));
+        else RBM_CUDA_TRY(launch_pdl(k_rnea_fast_soa_f32x2<SeqRigid, false>, g2, kBlock, 0, st, P, q, qd, qdd, tau, V, dV, n, ld));
+      }
+      return RBM_OK;
+    }
+  }
   if (m->path == PATH_SEQ_ISO) {
     if (tw) RBM_CUDA_TRY(launch_pdl(k_rnea_fast_soa<T, SeqIso, true>, grid, kBlock, 0, st, ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld));
     else RBM_CUDA_TRY(launch_pdl(k_rnea_fast_soa<T, SeqIso, false>, grid, kBlock, 0, st, ModelView<T>::fast(m), q, qd, qdd, tau, V, dV, n, ld));
