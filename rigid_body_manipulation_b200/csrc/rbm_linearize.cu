@@ -43,6 +43,7 @@ struct FastEval {
   }
   __device__ __forceinline__ void trig(const T (&q)[6], T (&c)[6], T (&s)[6]) const { fast_sincos<T, D>(q, c, s); }
   __device__ __forceinline__ static bool q_matters(int j) { return D::q_matters(j); }
+  __device__ __forceinline__ static bool qd_matters(int j) { return D::qd_matters(j); }
   __device__ __forceinline__ void id(const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6], const T (&qdd)[6], T (&tau)[6]) const {
     FastResult<T> r;
     fast_rnea_core<T, D, true>(P, P.g, q, c, s, qd, qdd, r);
@@ -77,6 +78,7 @@ struct GenericEval {
   __device__ __forceinline__ static bool is_hinge(int) { return false; }  // generic_rnea evaluates its own trigonometry
   __device__ __forceinline__ void trig(const T (&)[MAXJ], T (&)[MAXJ], T (&)[MAXJ]) const {}
   __device__ __forceinline__ static bool q_matters(int) { return true; }
+  __device__ __forceinline__ static bool qd_matters(int) { return true; }
   __device__ __forceinline__ void id(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qd)[MAXJ], const T (&qdd)[MAXJ],
                                      T (&tau)[MAXJ]) const {
     generic_rnea<T, 0>(sp, sp, nj_, q, qd, qdd, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -351,6 +353,16 @@ __device__ __forceinline__ void linearize_state(const E& ev, const T* __restrict
   // ---- velocity columns (velocity-product term only) ---------------------------------------------------------------------
 #pragma unroll 1
   for (int j = 0; j < nj; ++j) {
+    if (!E::qd_matters(j)) {  // d tau / d qd_j == 0 (Galilean invariance): the column of the pure integrator
+#pragma unroll
+      for (int r = 0; r < MJ; ++r) {
+        if (r < nj) {
+          A[((int64_t)r * ns + nj + j) * ld + s] = (r == j) ? dt : T(0);
+          A[((int64_t)(nj + r) * ns + nj + j) * ld + s] = (r == j) ? T(1) : T(0);
+        }
+      }
+      continue;
+    }
     T vp[MJ], vm[MJ], tp[MJ], tm[MJ];
 #pragma unroll
     for (int k = 0; k < MJ; ++k) {

@@ -43,6 +43,11 @@ struct SequentialDesc {
   // (The same dead-code argument is what lets nvcc drop those terms from the kernel.)  Used by the linearisation to skip
   // finite differences that are identically zero; verified against the oracle in tests/test_gpu_linearize.py.
   static constexpr bool q_matters(int j) { return j >= 3; }
+  // Does tau depend on qd_j?  Not for the gantry joints either: a constant translation velocity of the whole wrist is a Galilean
+  // boost (no rotation precedes those joints), so its contributions to G dV and ad(V)^T G V cancel identically -- numerically to
+  // ~1e-13 in the oracle.  The cancellation is between separately rounded terms, so the typed algebra cannot see it; it is
+  // declared here and checked against the oracle (tests/test_gpu_linearize.py::test_structure_of_the_euler_map).
+  static constexpr bool qd_matters(int j) { return j >= 3; }
 };
 using SeqIso = SequentialDesc<INERTIA_ISO>;
 using SeqRigid = SequentialDesc<INERTIA_RIGID>;

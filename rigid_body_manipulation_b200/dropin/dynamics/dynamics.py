@@ -24,7 +24,7 @@ import torch
 from numpy.typing import NDArray
 
 from rigid_body_manipulation_b200 import engine as _engine
-from rigid_body_manipulation_b200.lie import SE3, SO3, is_se3, se3_from_Rt
+from rigid_body_manipulation_b200.lie import SE3, is_se3, se3_from_Rt
 
 __all__ = [
     "StateSpaceConfig", "StateSpace", "get_spatial_inertia_matrix", "transfer_simat", "inverse",

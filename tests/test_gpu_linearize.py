@@ -63,8 +63,13 @@ def test_structure_of_the_euler_map():
     I = np.eye(6)
     assert np.abs(A[:, :6, :6] - (I + dt * A[:, 6:, :6])).max() < 1e-12
     assert np.abs(A[:, :6, 6:] - dt * A[:, 6:, 6:]).max() < 1e-12
-    # prismatic gantry: translations do not change the dynamics -> d qdd / d q_{0..2} == 0
+    # prismatic gantry: neither its positions nor (Galilean invariance) its velocities change the dynamics; the kernel skips those
+    # finite differences (SequentialDesc::q_matters / qd_matters) -- confirm with the literal transition-FD oracle
     assert np.abs(A[:, 6:, :3]).max() < 1e-6
+    assert np.abs(A[:, 6:, 6:9] - np.eye(6)[None, :, :3]).max() < 1e-6
+    Ar, _ = lo.transition_fd(consts_of(g), tr[:32, 0], tr[:32, 1], None, dt=dt, eps=1e-5)
+    assert np.abs(Ar[:, 6:, :3]).max() < 1e-8 and np.abs(Ar[:, 6:, 6:9] - np.eye(6)[None, :, :3]).max() < 1e-8
+    assert np.abs(A[:32] - Ar).max() < 2e-8
 
 
 def test_keyframe_linearisation_feeds_lqr():

@@ -3,7 +3,6 @@ extended precision -- the device code is the same source.  Skipped when nvcc is 
 import os
 import shutil
 import subprocess
-import sys
 
 import pytest
 
