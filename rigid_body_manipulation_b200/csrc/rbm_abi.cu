@@ -130,7 +130,7 @@ int rnea_host(const rbm_model* m, const T* traj_host, T* tau_host, int64_t n, in
   if (n == 0) return RBM_OK;
   if (!traj_host || !tau_host) return invalid("rbm_rnea_host: NULL buffer");
   const int nj = m->nj;
-  if (chunk <= 0) chunk = 1 << 18;
+  if (chunk <= 0) chunk = 1 << 16;  // measured best on B200 + PCIe Gen5 (tools/bench_e2e_chunk.py): short pipeline fill, copies still large
   if (chunk > n) chunk = n;
   DeviceGuard guard(m->device);
   RBM_CUDA_TRY(guard.status());
