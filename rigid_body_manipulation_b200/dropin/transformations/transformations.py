@@ -44,26 +44,30 @@ def tr2se3(t, r) -> SE3:
 
 
 def compose(trans: NDArray, rot: Optional[NDArray] = None) -> Union[SE3, list]:
-    if rot is None:
-        rot = np.array([[1, 0, 0, 0] for _ in trans])
-    single_trans = single_rot = False
-    if 1 == trans.ndim:
-        single_trans = True
-        trans = np.expand_dims(trans, 0)
-    if 1 == rot.ndim:
-        single_rot = True
-        rot = np.expand_dims(rot, 0)
-    assert len(trans) == len(rot), "Numbers of vectors in 'trans' and 'rot' must match."
-    poses = []
-    if len(trans) and rot.ndim == 2 and rot.shape[1] in (4, 9):
-        poses = _compose_rows(trans, rot)
-    else:  # ragged rows: same per-row dispatch as the reference (rows that are neither 4 nor 9 long are skipped)
-        for t, r in zip(trans, rot):
-            if 4 == len(r):
+    """Translations (3,) / (n, 3) with rotations given as wxyz quaternions (4,) / (n, 4) or flattened matrices (9,) / (n, 9) -> SE3.
+
+    Same contract as the reference: no `rot` means identity rotations; one translation with one rotation gives a single SE3,
+    anything else a list; mismatched counts raise AssertionError; invalid quaternions / matrices raise ValueError.
+    """
+    trans = np.asarray(trans)
+    rot = np.tile(np.array([1, 0, 0, 0]), (len(trans), 1)) if rot is None else np.asarray(rot)
+    scalar_result = trans.ndim == 1 and rot.ndim == 1
+    trans2d = trans[None] if trans.ndim == 1 else trans
+    rot2d = rot[None] if rot.ndim == 1 else rot
+    assert len(trans2d) == len(rot2d), "Numbers of vectors in 'trans' and 'rot' must match."
+    if len(trans2d) and rot2d.ndim == 2 and rot2d.shape[1] in (4, 9):
+        poses = _compose_rows(trans2d, rot2d)  # one launch for the whole register
+    else:
+        # ragged rotation rows: per-row dispatch on the row length; rows that are neither quaternions nor matrices are dropped,
+        # as the reference does
+        poses = []
+        for t, r in zip(trans2d, rot2d):
+            r = np.asarray(r)
+            if r.size == 4:
                 poses.append(tq2se3(t, r))
-            elif 9 == len(r):
-                poses.append(tr2se3(t, np.asarray(r).reshape(3, 3)))
-    return poses[0] if single_trans and single_rot else poses
+            elif r.size == 9:
+                poses.append(tr2se3(t, r.reshape(3, 3)))
+    return poses[0] if scalar_result else poses
 
 
 def homogenize(coord, forth_val=1):
