@@ -122,6 +122,10 @@ class StateSpace:
         return self._model
 
     def update_matrices(self, m, d) -> None:
+        if not isinstance(m, _engine.Model) and not hasattr(m, "hposes_Rt"):
+            from rigid_body_manipulation_b200.mujoco_bridge import refresh_kinematics
+
+            refresh_kinematics(m, d)  # mjd_transitionFD leaves d evaluated at the current state; callers rely on it
         model = self._engine_model(m, d)
         dt = float(getattr(getattr(m, "opt", None), "timestep", getattr(m, "timestep", 0.002)))
         dev = model.device

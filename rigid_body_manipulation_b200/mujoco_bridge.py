@@ -14,9 +14,25 @@ from .lie import SE3
 SLIDE, HINGE = 2, 3  # mjtJoint
 
 
+def refresh_kinematics(m, d) -> bool:
+    """For real MuJoCo objects: run mj_forward so that d.xpos / xmat / xipos / site_x* describe the current qpos.  The reference
+    relies on mjd_transitionFD (inside the LQR constructor, controllers/lqr.py:34-36) for this side effect before simulate()
+    reads the world poses; the replacement StateSpace must therefore provide it.  Returns False for look-alike objects."""
+    try:
+        import mujoco
+    except ImportError:
+        return False
+    if isinstance(m, mujoco.MjModel) and isinstance(d, mujoco.MjData):
+        mujoco.mj_forward(m, d)
+        return True
+    return False
+
+
 def constants_from_mujoco(m, d, last_link="link6", object_body="target/object", sensor_site="target/ft_sensor") -> dict:
     from .dropin.dynamics import get_spatial_inertia_matrix, transfer_simat
     from .dropin.transformations.poses import Poses, _element_id
+
+    refresh_kinematics(m, d)
 
     poses = Poses(m, d)
     id_ll = _element_id(m, "body", last_link)
