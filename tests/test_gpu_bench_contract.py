@@ -1,0 +1,65 @@
+"""-m gpu: bench.py honours the driver's JSON contract (keys, types, roofline / e2e / cpu_baseline objects) for every workload
+and for the reference arm.  Small sizes so that the whole file runs in well under a minute."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+             "config", "e2e", "gpu_launches"}
+
+
+def run_bench(*args):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    return json.loads(lines[0])
+
+
+def check_common(d):
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    assert isinstance(d["config"], dict) and "workload" in d["config"] and "model" not in d["config"]
+    e = d["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e) and e["value"] > 0
+
+
+def test_default_workload_line():
+    d = run_bench("--steps", "5", "--warmup", "3", "--samples", "262144", "--cpu-samples", "256")
+    check_common(d)
+    assert d["metric"] == "rnea_samples_per_s" and d["unit"] == "samples/s" and d["dtype"] == "f64" and d["n_gpus"] == 1
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert r["algorithmic_bytes_per_launch"] == 192 * 262144
+    assert d["gpu_launches"] == 5
+    assert d["e2e"]["h2d_bytes_per_step"] == 144 * 262144 and d["e2e"]["d2h_bytes_per_step"] == 48 * 262144
+    assert d["e2e"]["value"] < d["value"]  # host copies are inside the e2e timed region
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    k = d["clocks"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(k)
+    assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(k["reasons"]))
+
+
+@pytest.mark.parametrize("extra", [("--dtype", "f32"), ("--workload", "gram", "--samples", "262144"), ("--workload", "gram", "--dtype", "f32", "--samples", "262144"),
+                                   ("--workload", "linearize", "--samples", "65536")])
+def test_other_workloads(extra):
+    d = run_bench("--steps", "3", "--warmup", "3", "--no-cpu", *extra)
+    check_common(d)
+    assert 0 < d["roofline"]["frac"] < 2
+
+
+def test_reference_arm_line():
+    d = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--cpu-samples", "128")
+    check_common(d)
+    assert d["impl"] == "reference" and d["metric"] == "rnea_samples_per_s" and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port"
