@@ -340,10 +340,20 @@ def run_gpu_arm(args):
         wl.step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # how many untimed steps fill ~0.3 s (so that the clock sampler sees loaded clocks).  The count must be IDENTICAL on every
+    # rank -- a step may contain a collective (Gram all-reduce) -- so it is derived from a max-reduced estimate, never from a
+    # per-rank wall-clock loop.
+    t0 = time.perf_counter()
+    for _ in range(3):
+        wl.step()
+    torch.cuda.synchronize()
+    est = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    n_heat = int(min(20000, max(10, 0.3 / max(est.item(), 1e-6))))
+    barrier()
     with ClockSampler(local) as clk:
-        # untimed launches first so that the sampler sees loaded clocks (>= ~0.3 s)
-        t_end = time.perf_counter() + 0.3
-        while time.perf_counter() < t_end:
+        for _ in range(n_heat):
             wl.step()
         # pass 1 -- the reported value: exactly K steps back to back, bracketed by barrier + synchronize
         barrier()
