@@ -77,6 +77,15 @@ RBM_API int rbm_model_create(int nj, const double* hposes_Rt, const double* sima
                      const double* dtwist_0, const double* wrench_tip, const double* pose_tip_Rt, const double* pose_sen_Rt,
                      unsigned flags, int device, rbm_model** out);
 RBM_API void rbm_model_destroy(rbm_model* m);
+/* Device-free analysis of the same constants (needs no GPU): which kernel path the model takes and the parameter blocks the
+ * kernels would receive -- fast_params [rbm_fast_param_count()] (the structure-specialised kernels' constant block, zeros when the
+ * path is generic) and generic_params [rbm_generic_param_count(nj)] (the shared-memory block of the generic kernels).  Any output
+ * pointer may be NULL.  Validation and error codes are those of rbm_model_create. */
+RBM_API int rbm_model_analyze(int nj, const double* hposes_Rt, const double* simats, const double* uscrews, const double* twist_0,
+                      const double* dtwist_0, const double* wrench_tip, const double* pose_tip_Rt, const double* pose_sen_Rt,
+                      unsigned flags, int* kernel_path, double* fast_params, double* generic_params);
+RBM_API int rbm_fast_param_count(void);
+RBM_API int rbm_generic_param_count(int nj);
 RBM_API int rbm_model_num_joints(const rbm_model* m);
 RBM_API int rbm_model_kernel_path(const rbm_model* m);
 

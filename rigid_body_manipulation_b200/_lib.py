@@ -47,6 +47,9 @@ SIGNATURES = {
     "rbm_device_count": (C.c_int, []),
     "rbm_model_create": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint, C.c_int, C.POINTER(_vp)]),
     "rbm_model_destroy": (None, [_vp]),
+    "rbm_model_analyze": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint, C.POINTER(C.c_int), _vp, _vp]),
+    "rbm_fast_param_count": (C.c_int, []),
+    "rbm_generic_param_count": (C.c_int, [C.c_int]),
     "rbm_model_num_joints": (C.c_int, [_vp]),
     "rbm_model_kernel_path": (C.c_int, [_vp]),
     "rbm_rnea_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),

@@ -188,29 +188,29 @@ int rbm_device_count(void) {
   return n;
 }
 
-int rbm_model_create(int nj, const double* hposes_Rt, const double* simats, const double* uscrews, const double* twist_0,
-                     const double* dtwist_0, const double* wrench_tip, const double* pose_tip_Rt, const double* pose_sen_Rt,
-                     unsigned flags, int device, rbm_model** out) {
-  if (!out) return invalid("rbm_model_create: out is NULL");
-  *out = nullptr;
-  if (nj < 1) return invalid("rbm_model_create: nj must be >= 1");
+}  // extern "C"
+
+namespace {
+// Device-free part of model creation: validation, generic packing, structure analysis.  Fills everything of `m` except the
+// device buffers.
+int analyze_model(const char* who, int nj, const double* hposes_Rt, const double* simats, const double* uscrews, const double* twist_0,
+                  const double* dtwist_0, const double* wrench_tip, const double* pose_tip_Rt, const double* pose_sen_Rt, unsigned flags,
+                  rbm_model* m) {
+  const std::string w(who);
+  if (nj < 1) return invalid(w + ": nj must be >= 1");
   if (nj > RBM_MAX_JOINTS) {
-    set_error("rbm_model_create: nj exceeds RBM_MAX_JOINTS (16)");
+    set_error(w + ": nj exceeds RBM_MAX_JOINTS (16)");
     return RBM_ERR_UNSUPPORTED;
   }
-  if (!hposes_Rt || !simats || !uscrews || !twist_0 || !dtwist_0) return invalid("rbm_model_create: NULL constant array");
+  if (!hposes_Rt || !simats || !uscrews || !twist_0 || !dtwist_0) return invalid(w + ": NULL constant array");
   const int np = generic_param_count(nj);
   for (int i = 0; i < (nj + 1) * 12; ++i)
-    if (!std::isfinite(hposes_Rt[i])) return invalid("rbm_model_create: non-finite home pose");
+    if (!std::isfinite(hposes_Rt[i])) return invalid(w + ": non-finite home pose");
   for (int i = 0; i < (nj + 1) * 36; ++i)
-    if (!std::isfinite(simats[i])) return invalid("rbm_model_create: non-finite spatial inertia");
+    if (!std::isfinite(simats[i])) return invalid(w + ": non-finite spatial inertia");
   for (int i = 0; i < nj * 6; ++i)
-    if (!std::isfinite(uscrews[i])) return invalid("rbm_model_create: non-finite screw");
-
-  rbm_model* m = new (std::nothrow) rbm_model();
-  if (!m) return invalid("rbm_model_create: out of host memory");
+    if (!std::isfinite(uscrews[i])) return invalid(w + ": non-finite screw");
   m->nj = nj;
-  m->device = device;
   m->no_tma = (flags & RBM_FLAG_NO_TMA) != 0;
   m->gp64.assign(np, 0.0);
   double* g = m->gp64.data();
@@ -224,10 +224,10 @@ int rbm_model_create(int nj, const double* hposes_Rt, const double* simats, cons
     double* J = g + GP_HEAD + GJ_STRIDE * i;
     std::memcpy(J + GJ_HR, hposes_Rt + 12 * (i + 1), 12 * sizeof(double));
     std::memcpy(J + GJ_S, uscrews + 6 * i, 6 * sizeof(double));
-    const double* w = uscrews + 6 * i + 3;
-    const double wn = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    const double* ax = uscrews + 6 * i + 3;
+    const double wn = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
     J[GJ_WN] = wn;
-    for (int k = 0; k < 3; ++k) J[GJ_AXIS + k] = wn > 0.0 ? w[k] / wn : 0.0;
+    for (int k = 0; k < 3; ++k) J[GJ_AXIS + k] = wn > 0.0 ? ax[k] / wn : 0.0;
     std::memcpy(J + GJ_G, simats + 36 * (i + 1), 36 * sizeof(double));
   }
   m->gp32.resize(np);
@@ -254,7 +254,41 @@ int rbm_model_create(int nj, const double* hposes_Rt, const double* simats, cons
         for (int c = 0; c < 3; ++c) m->fp64.senR[3 * r + c] = r == c ? (m->fp64.senR[3 * r + c] > 0 ? 1.0 : -1.0) : 0.0;
   }
   convert_fast(m->fp64, &m->fp32);
+  return RBM_OK;
+}
+}  // namespace
 
+extern "C" {
+
+int rbm_fast_param_count(void) { return (int)(sizeof(FastParams<double>) / sizeof(double)); }
+int rbm_generic_param_count(int nj) { return (nj < 1 || nj > RBM_MAX_JOINTS) ? RBM_ERR_INVALID : generic_param_count(nj); }
+
+int rbm_model_analyze(int nj, const double* hposes_Rt, const double* simats, const double* uscrews, const double* twist_0, const double* dtwist_0,
+                      const double* wrench_tip, const double* pose_tip_Rt, const double* pose_sen_Rt, unsigned flags, int* kernel_path,
+                      double* fast_params, double* generic_params) {
+  rbm_model tmp;
+  int rc = analyze_model("rbm_model_analyze", nj, hposes_Rt, simats, uscrews, twist_0, dtwist_0, wrench_tip, pose_tip_Rt, pose_sen_Rt, flags, &tmp);
+  if (rc != RBM_OK) return rc;
+  if (kernel_path) *kernel_path = tmp.path;
+  if (fast_params) std::memcpy(fast_params, &tmp.fp64, sizeof(tmp.fp64));
+  if (generic_params) std::memcpy(generic_params, tmp.gp64.data(), tmp.gp64.size() * sizeof(double));
+  return RBM_OK;
+}
+
+int rbm_model_create(int nj, const double* hposes_Rt, const double* simats, const double* uscrews, const double* twist_0,
+                     const double* dtwist_0, const double* wrench_tip, const double* pose_tip_Rt, const double* pose_sen_Rt,
+                     unsigned flags, int device, rbm_model** out) {
+  if (!out) return invalid("rbm_model_create: out is NULL");
+  *out = nullptr;
+  rbm_model* m = new (std::nothrow) rbm_model();
+  if (!m) return invalid("rbm_model_create: out of host memory");
+  int rc = analyze_model("rbm_model_create", nj, hposes_Rt, simats, uscrews, twist_0, dtwist_0, wrench_tip, pose_tip_Rt, pose_sen_Rt, flags, m);
+  if (rc != RBM_OK) {
+    delete m;
+    return rc;
+  }
+  m->device = device;
+  const int np = generic_param_count(nj);
   DeviceGuard guard(device);
   cudaError_t e = guard.status();
   if (e == cudaSuccess) e = cudaMalloc(&m->d_gp64, np * sizeof(double));
@@ -262,7 +296,7 @@ int rbm_model_create(int nj, const double* hposes_Rt, const double* simats, cons
   if (e == cudaSuccess) e = cudaMemcpy(m->d_gp64, m->gp64.data(), np * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(m->d_gp32, m->gp32.data(), np * sizeof(float), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
-    int rc = cuda_fail(e, "rbm_model_create (device allocation / upload)");
+    rc = cuda_fail(e, "rbm_model_create (device allocation / upload)");
     cudaGetLastError();
     rbm_model_destroy(m);
     return rc;

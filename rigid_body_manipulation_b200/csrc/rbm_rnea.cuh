@@ -336,7 +336,7 @@ RBM_HD void adjointT_apply(const T* R, G3<T> p, G3<T> f, G3<T> m, G3<T>& fo, G3<
 // survive until the backward sweep.  Optional full-state outputs mirror the reference's return value
 // (tau, poses, twists, dtwists) for the scalar drop-in API.
 template <class T, int NJ>
-__device__ __forceinline__ void generic_rnea(const T* __restrict__ sp, const T* __restrict__ base /* [V0 | dV0 | Ftip], normally == sp */, int nj_rt, const T* q, const T* qd, const T* qdd, T* tau,
+RBM_HD void generic_rnea(const T* __restrict__ sp, const T* __restrict__ base /* [V0 | dV0 | Ftip], normally == sp */, int nj_rt, const T* q, const T* qd, const T* qdd, T* tau,
                                              T* poses /* [nj][12] or null */, T* twists /* [nj+1][6] or null */, T* dtwists /* idem */,
                                              T* Vlast /* [6] or null */, T* dVlast /* [6] or null */) {
   constexpr int MAXJ = NJ > 0 ? NJ : RBM_MAX_JOINTS;

@@ -49,6 +49,28 @@ def _ptr(a):
     return C.c_void_p(a.data_ptr())
 
 
+def analyze_model(hposes_body_parent, simats_body, uscrews_body, twist_0, dtwist_0, wrench_tip=None, pose_tip_ee=None, pose_sen_llj=None,
+                  force_generic=False):
+    """Device-free model analysis (rbm_model_analyze; works without a GPU): the kernel path the constants select and the parameter
+    blocks the kernels would receive.  Returns (path_name, fast_params ndarray, generic_params ndarray)."""
+    lib = _lib.load()
+    uscrews = _f64(uscrews_body)
+    nj = uscrews.shape[0]
+    Rt = poses_to_Rt(hposes_body_parent)
+    simats = _f64(simats_body)
+    if Rt.shape != (nj + 1, 12) or simats.shape != (nj + 1, 6, 6):
+        raise ValueError(f"need nj+1 = {nj + 1} home poses and spatial inertias")
+    opt = lambda a, conv: None if a is None else conv(a)
+    wt, tip, sen = opt(wrench_tip, lambda a: _f64(a, (6,))), opt(pose_tip_ee, pose_to_Rt), opt(pose_sen_llj, pose_to_Rt)
+    path = C.c_int(-1)
+    fast = np.zeros(lib.rbm_fast_param_count())
+    generic = np.zeros(max(lib.rbm_generic_param_count(nj), 0))
+    rc = lib.rbm_model_analyze(nj, _ptr(Rt), _ptr(simats), _ptr(uscrews), _ptr(_f64(twist_0, (6,))), _ptr(_f64(dtwist_0, (6,))), _ptr(wt), _ptr(tip),
+                               _ptr(sen), _lib.FLAG_FORCE_GENERIC if force_generic else 0, C.byref(path), _ptr(fast), _ptr(generic))
+    _lib.check(rc, "rbm_model_analyze")
+    return _lib.PATH_NAMES[path.value], fast, generic
+
+
 class Model:
     """Device-resident model constants (opaque `rbm_model*`) for one CUDA device."""
 

@@ -1,0 +1,117 @@
+// TEST INFRASTRUCTURE ONLY (never part of librbm_b200.so, never reachable from the package).
+//
+// The device arithmetic of the kernels lives in __host__ __device__ headers (csrc/rbm_typed.cuh, rbm_trig.cuh, rbm_rnea.cuh).
+// This translation unit instantiates the SAME per-sample functions for the host and exposes them through a tiny C interface,
+// so that the `-m "not gpu"` suite can check the kernels' mathematics -- the structure-specialised typed recursion, the generic
+// recursion, the regressor blocks, the reduced (inertia-only / velocity-only) evaluations -- against the reference-generated
+// golden vectors on a machine without a GPU.  It proves nothing about launches, memory traffic or TMA pipelines; the -m gpu
+// suite does that through the real C ABI.
+#include <cstdint>
+#include <cstring>
+
+#include "rbm_rnea.cuh"
+
+using namespace rbm;
+
+namespace {
+template <class T, class D, bool VEL, bool GRAV, bool ACC>
+void run_fast(const FastParams<T>& P, const T* traj, T* tau, T* V, T* dV, int64_t n) {
+  for (int64_t s = 0; s < n; ++s) {
+    T q[6], qd[6], qdd[6], c[6], sn[6];
+    for (int j = 0; j < 6; ++j) { q[j] = traj[s * 18 + j]; qd[j] = traj[s * 18 + 6 + j]; qdd[j] = traj[s * 18 + 12 + j]; }
+    fast_sincos<T, D>(q, c, sn);
+    FastResult<T> r;
+    fast_rnea_core<T, D, true, VEL, GRAV, ACC>(P, P.g, q, c, sn, qd, qdd, r);
+    for (int j = 0; j < 6; ++j) tau[s * 6 + j] = r.tau[j];
+    if (V) {
+      for (int k = 0; k < 3; ++k) { V[s * 6 + k] = r.v[k]; V[s * 6 + 3 + k] = r.w[k]; dV[s * 6 + k] = r.a[k]; dV[s * 6 + 3 + k] = r.l[k]; }
+    }
+  }
+}
+
+template <class T>
+FastParams<T> convert(const double* fp) {
+  FastParams<T> P;
+  T* dst = reinterpret_cast<T*>(&P);
+  for (size_t i = 0; i < sizeof(FastParams<double>) / sizeof(double); ++i) dst[i] = (T)fp[i];
+  return P;
+}
+
+// mode: 0 = full ID, 1 = inertia-only (VEL off, GRAV off), 2 = velocity-product only (ACC off, GRAV off)
+template <class T>
+int fast_dispatch(int path, int mode, const double* fp, const T* traj, T* tau, T* V, T* dV, int64_t n) {
+  const FastParams<T> P = convert<T>(fp);
+#define RUN(D)                                                                  \
+  if (mode == 0) run_fast<T, D, true, true, true>(P, traj, tau, V, dV, n);      \
+  else if (mode == 1) run_fast<T, D, false, false, true>(P, traj, tau, V, dV, n); \
+  else if (mode == 2) run_fast<T, D, true, false, false>(P, traj, tau, V, dV, n); \
+  else return -1;
+  if (path == PATH_SEQ_ISO) { RUN(SeqIso) }
+  else if (path == PATH_SEQ_RIGID) { RUN(SeqRigid) }
+  else return -1;
+#undef RUN
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int h_fast_rnea_f64(int path, int mode, const double* fast_params, const double* traj, double* tau, double* V, double* dV, int64_t n) {
+  return fast_dispatch<double>(path, mode, fast_params, traj, tau, V, dV, n);
+}
+int h_fast_rnea_f32(int path, int mode, const double* fast_params, const float* traj, float* tau, float* V, float* dV, int64_t n) {
+  return fast_dispatch<float>(path, mode, fast_params, traj, tau, V, dV, n);
+}
+
+// generic recursion; gp = packed generic parameters (rbm_model_analyze), unrolled != 0 uses the compile-time nj = 6 instance
+int h_generic_rnea_f64(const double* gp, int nj, int unrolled, const double* traj, double* tau, double* poses, double* twists, double* dtwists,
+                       double* Vlast, double* dVlast, int64_t n) {
+  if (nj < 1 || nj > RBM_MAX_JOINTS || (unrolled && nj != 6)) return -1;
+  for (int64_t s = 0; s < n; ++s) {
+    double q[RBM_MAX_JOINTS], qd[RBM_MAX_JOINTS], qdd[RBM_MAX_JOINTS], t[RBM_MAX_JOINTS];
+    for (int j = 0; j < nj; ++j) { q[j] = traj[s * 3 * nj + j]; qd[j] = traj[s * 3 * nj + nj + j]; qdd[j] = traj[s * 3 * nj + 2 * nj + j]; }
+    double* P = poses ? poses + s * nj * 12 : nullptr;
+    double* TW = twists ? twists + s * (nj + 1) * 6 : nullptr;
+    double* DTW = dtwists ? dtwists + s * (nj + 1) * 6 : nullptr;
+    double* VL = Vlast ? Vlast + s * 6 : nullptr;
+    double* DVL = dVlast ? dVlast + s * 6 : nullptr;
+    if (unrolled) generic_rnea<double, 6>(gp, gp, nj, q, qd, qdd, t, P, TW, DTW, VL, DVL);
+    else generic_rnea<double, 0>(gp, gp, nj, q, qd, qdd, t, P, TW, DTW, VL, DVL);
+    for (int j = 0; j < nj; ++j) tau[s * nj + j] = t[j];
+  }
+  return 0;
+}
+
+int h_generic_rnea_f32(const double* gp, int nj, const float* traj, float* tau, int64_t n) {
+  if (nj < 1 || nj > RBM_MAX_JOINTS) return -1;
+  const int np = GP_HEAD + GJ_STRIDE * nj;
+  float gpf[GP_HEAD + GJ_STRIDE * RBM_MAX_JOINTS];
+  for (int i = 0; i < np; ++i) gpf[i] = (float)gp[i];
+  for (int64_t s = 0; s < n; ++s) {
+    float q[RBM_MAX_JOINTS], qd[RBM_MAX_JOINTS], qdd[RBM_MAX_JOINTS], t[RBM_MAX_JOINTS];
+    for (int j = 0; j < nj; ++j) { q[j] = traj[s * 3 * nj + j]; qd[j] = traj[s * 3 * nj + nj + j]; qdd[j] = traj[s * 3 * nj + 2 * nj + j]; }
+    generic_rnea<float, 0>(gpf, gpf, nj, q, qd, qdd, t, nullptr, nullptr, nullptr, nullptr, nullptr);
+    for (int j = 0; j < nj; ++j) tau[s * nj + j] = t[j];
+  }
+  return 0;
+}
+
+// sensor-frame twists + regressor rows: V, dV [n][6] -> Y [n][6][10]
+int h_sensor_regressor_f64(const double* pose_Rt, const double* V, const double* dV, double* Vs, double* dVs, double* Y, int64_t n) {
+  for (int64_t s = 0; s < n; ++s) {
+    double vs[6], dvs[6], top[3][4], bot[3][9];
+    sensor_twists(pose_Rt, pose_Rt + 9, V + 6 * s, dV + 6 * s, vs, dvs);
+    regressor_blocks(vs, dvs, top, bot);
+    std::memcpy(Vs + 6 * s, vs, sizeof(vs));
+    std::memcpy(dVs + 6 * s, dvs, sizeof(dvs));
+    double* y = Y + 60 * s;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 10; ++c) {
+        y[r * 10 + c] = c < 4 ? top[r][c] : 0.0;
+        y[(3 + r) * 10 + c] = c == 0 ? 0.0 : bot[r][c - 1];
+      }
+  }
+  return 0;
+}
+
+}  // extern "C"
