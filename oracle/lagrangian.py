@@ -86,18 +86,104 @@ def mass_matrix_and_potential(consts, q):
 
 
 def lagrangian_tau(consts, q, qd, qdd, h=1e-6):
+    """`consts` is the dict of Newton-Euler constants, or any callable q -> (M(q), U(q)) (e.g. `mjcf_mass_matrix_and_potential`)."""
     q, qd, qdd = (np.asarray(a, float) for a in (q, qd, qdd))
     nj = len(q)
-    M, _ = mass_matrix_and_potential(consts, q)
+    if callable(consts):
+        mass_matrix_and_potential = consts  # noqa: F811 -- same contract, other source of M and U
+        consts = None
+    else:
+        mass_matrix_and_potential = globals()["mass_matrix_and_potential"]
+    M, _ = mass_matrix_and_potential(consts, q) if consts is not None else mass_matrix_and_potential(q)
     dM = np.zeros((nj, nj, nj))  # dM[k] = dM/dq_k
     dU = np.zeros(nj)
     for k in range(nj):
         e = np.zeros(nj)
         e[k] = h
-        Mp, Up = mass_matrix_and_potential(consts, q + e)
-        Mm, Um = mass_matrix_and_potential(consts, q - e)
+        Mp, Up = mass_matrix_and_potential(consts, q + e) if consts is not None else mass_matrix_and_potential(q + e)
+        Mm, Um = mass_matrix_and_potential(consts, q - e) if consts is not None else mass_matrix_and_potential(q - e)
         dM[k] = (Mp - Mm) / (2 * h)
         dU[k] = (Up - Um) / (2 * h)
     Mdot = np.einsum("kij,k->ij", dM, qd)
     quad = 0.5 * np.einsum("kij,i,j->k", dM, qd, qd)
     return M @ qdd + Mdot @ qd - quad + dU
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# M(q), U(q) straight from an MJCF text (MuJoCo's documented body / joint / inertial semantics), bypassing every
+# Newton-Euler constant: used to check `rigid_body_manipulation_b200.mjcf_export.to_mjcf` without MuJoCo.
+# ---------------------------------------------------------------------------------------------------------------------
+def _quat_R(q):
+    w, x, y, z = np.asarray(q, float) / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def mjcf_mass_matrix_and_potential(xml_text):
+    """Returns f(q) -> (M, U) for a tree given as MJCF text with quat-only frames (what `to_mjcf` writes).
+
+    MuJoCo semantics: a body frame is (pos, quat) in its parent; its joint moves the body relative to the parent about / along
+    `axis` (body coordinates) through the anchor `pos` (body coordinates); `inertial` is (pos, quat, mass, diaginertia) in the body."""
+    import xml.etree.ElementTree as ET
+
+    root = ET.fromstring(xml_text)
+    fl = lambda s, d: np.array([float(x) for x in s.split()]) if s is not None else np.array(d, float)  # noqa: E731
+    g = fl(root.find("option").get("gravity"), [0, 0, -9.81])
+    bodies = []  # (parent index, pos, R, joint or None, inertial or None)
+
+    def walk(elem, parent):
+        for b in elem.findall("body"):
+            j, it = b.find("joint"), b.find("inertial")
+            jt = None if j is None else (j.get("type", "hinge"), fl(j.get("axis"), [0, 0, 1]), fl(j.get("pos"), [0, 0, 0]))
+            inert = None if it is None else (float(it.get("mass")), fl(it.get("pos"), [0, 0, 0]), _quat_R(fl(it.get("quat"), [1, 0, 0, 0])),
+                                             fl(it.get("diaginertia"), [0, 0, 0]))
+            bodies.append((parent, fl(b.get("pos"), [0, 0, 0]), _quat_R(fl(b.get("quat"), [1, 0, 0, 0])), jt, inert))
+            walk(b, len(bodies) - 1)
+
+    walk(root.find("worldbody"), -1)
+    nq = sum(1 for b in bodies if b[3] is not None)
+
+    def f(q):
+        frames, joints, k = [], [], 0  # joints: (kind, world axis, world anchor, body index)
+        for parent, pos, R, jt, _ in bodies:
+            Rp, pp = (np.eye(3), np.zeros(3)) if parent < 0 else frames[parent]
+            Rb, pb = Rp @ R, Rp @ pos + pp
+            if jt is not None:
+                kind, axis, anchor = jt
+                a_w, anc_w = Rb @ axis, Rb @ anchor + pb
+                if kind == "slide":
+                    pb = pb + a_w * q[k]
+                    anc_w = anc_w + a_w * q[k]
+                else:
+                    Rj = expm(_hat(a_w) * q[k])
+                    Rb, pb = Rj @ Rb, anc_w + Rj @ (pb - anc_w)
+                joints.append((kind, a_w, anc_w, len(frames)))
+                k += 1
+            frames.append((Rb, pb))
+        # ancestors
+        M, U = np.zeros((nq, nq)), 0.0
+        for bi, (parent, _, _, _, inert) in enumerate(bodies):
+            if inert is None:
+                continue
+            m, ipos, iR, diag = inert
+            Rb, pb = frames[bi]
+            pc, Rc = Rb @ ipos + pb, Rb @ iR
+            anc, a = set(), bi
+            while a >= 0:
+                anc.add(a)
+                a = bodies[a][0]
+            Jv, Jw = np.zeros((3, nq)), np.zeros((3, nq))
+            for col, (kind, a_w, anc_w, jb) in enumerate(joints):
+                if jb not in anc:
+                    continue
+                if kind == "slide":
+                    Jv[:, col] = a_w
+                else:
+                    Jw[:, col] = a_w
+                    Jv[:, col] = np.cross(a_w, pc - anc_w)
+            M += m * Jv.T @ Jv + Jw.T @ (Rc @ np.diag(diag) @ Rc.T) @ Jw
+            U -= m * g @ pc
+        return M, U
+
+    return f
