@@ -284,6 +284,13 @@ __global__ void __launch_bounds__(kGramBlock, 1) k_regressor_gram(const __grid_c
 //   same + "last warp to drain refills" instead of a CTA barrier   20.8 / 34.6   (the barrier was not the limiter)
 //   per-warp pipelines with 256-byte copies               17.6 / 26.5   (8x more copies: TMA-issue bound)
 //   TMA, the 24 copies spread over the 8 warps (this code) 23.9 / 42.6
+// Two later restructurings, both bit-identical and both rejected on measurement (tools/kbench, 12.5 M samples, 200 launches,
+// fp64: this code 29.0 G samples/s at burst clocks):
+//   per-stage `empty` mbarriers + refill one tile late instead of __syncthreads (warps free to drift 3 tiles)   28.8 (fp32 45.6 vs 47.0)
+//   warp-specialised: 8 kinematics warps (setmaxnreg 128) hand [V_s | dV_s | f] through shared memory to
+//     4 accumulator warps (setmaxnreg 240, one per scheduler, 2 samples per tile each)                           25.3 ... 26.9
+// i.e. neither the CTA barrier nor the lock-step phases are the limiter; the FP64 pipe is ~60 % busy and what is left is
+// dependent-issue latency inside each thread, which only more resident warps (registers!) or less arithmetic would remove.
 // In fp64 the kernel is then bound by the FP64 pipe at 8 warps per SM (250 registers: 70 double accumulators).
 constexpr int kStreams = 24;  // q(6) qd(6) qdd(6) f(6)
 constexpr int kGramStages = 4;
@@ -312,7 +319,6 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
 
   // Issue cost of a bulk copy is paid by the issuing warp, so the 24 copies of a tile are spread over the 8 warps: lane 0 of
   // warp w brings streams w, w + 8, w + 16 and announces their bytes on the stage's barrier.
-  const T* const stream_base[4] = {q, qd, qdd, f};
   auto issue = [&](int64_t it) {
     const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
     if (tile >= nfull) return;
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int k = warp + 8 * i;  // stream index 0..23 = array (k / 6), row (k % 6)
-      bulk_copy_g2s(dst + k * kGramBlock, stream_base[k / 6] + (int64_t)(k % 6) * ld + s0, kRowBytes, bar);
+      bulk_copy_g2s(dst + k * kGramBlock, (k < 6 ? q : k < 12 ? qd : k < 18 ? qdd : f) + (int64_t)(k % 6) * ld + s0, kRowBytes, bar);
     }
   };
   if (lane == 0) {
