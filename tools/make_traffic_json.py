@@ -10,7 +10,7 @@ SOURCES = {
     "rnea_f32_1048576": "r1c_rnea_f32_ncu_full.csv",
     "gram_f64_12500000": "r1c_gram_f64_ncu_full.csv",
     "gram_f32_12500000": "r1b_gram_f32_ncu_full.csv",
-    "linearize_f64_1048576": "r1c_linearize_ncu_full.csv",
+    "linearize_f64_1048576": "r1d_linearize_ncu_full.csv",
 }
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
