@@ -198,6 +198,24 @@ RBM_API int rbm_linearize_f64(const rbm_model* m, const double* q, const double*
 RBM_API int rbm_forward_dynamics_f64(const rbm_model* m, const double* q, const double* qd, const double* u, double dt, double* qdd, double* q_next,
                              double* qd_next, int64_t n, int64_t ld, void* stream);
 
+/* ---- closed-loop replay (reference core/simulate.py:185-270), n environments per launch, one per thread ---------------
+ * The reference's main loop with mj_step replaced by the transition above.  Per step: tgt = plan(step) (quintic profile as in
+ * rbm_rnea_planned_*), tgt_ctrl = ID(tgt) (:187-188); act = (qpos, qvel, qacc of the PREVIOUS forward pass) (:191-194);
+ * res = [(tgt_q - qpos) / pos_residual_divisor, tgt_qd - qvel] (mj_differentiatePos is called with m.nu in its dt slot: pass nu
+ * = 6 to replay the reference, 1 for the plain difference) (:257-265);  ctrl = tgt_ctrl - gain res (:268);  forward pass + semi-
+ * implicit Euler (:270).  On frame steps (`frame_count <= time * fps`, :196) a record
+ *   [act (3 nj) | V_s (6) | dV_s (6) | wrench (6)]
+ * is written: sensor-frame twists of act (:202-209) and the F/T reading left by the previous forward pass (:218-221), modelled
+ * as the Newton-Euler wrench Y(V_s, dV_s) phi_sensed of the sensed subtree (MuJoCo: cfrc_int of the site's body).  The loop
+ * starts from one forward pass at (q0, qd0) with ctrl = 0.
+ *   plan_coeffs (6), displacement (nj), pos_offset (nj): HOST;  gain [nj][2 nj] row-major, phi_sensed (10): DEVICE
+ *   q0, qd0 (or NULL = rest): [nj][ld] device;  frames: [max_frames][3 nj + 18][ld] device (frames beyond max_frames are dropped)
+ *   frame_steps [max_frames], n_frames [1]: device int32 or NULL;  final_state [3 nj][ld] (qpos, qvel, qacc) or NULL */
+RBM_API int rbm_closed_loop_f64(const rbm_model* m, const double* plan_coeffs, const double* displacement, const double* pos_offset, double plan_timestep,
+                        double init_step, int64_t n_steps, const double* gain, const double* phi_sensed, double dt, double fps,
+                        double pos_residual_divisor, const double* q0, const double* qd0, double* frames, int64_t max_frames, int32_t* frame_steps,
+                        int32_t* n_frames, double* final_state, int64_t n, int64_t ld, void* stream);
+
 /* ---- frame algebra helpers, batched (device pointers, AoS) ----------------------------------------------
  * transfer_simat (dynamics/dynamics.py:72-106): out[s] = Ad(T_s^-1)^T G_s Ad(T_s^-1); poses [n][12], simats [n][36]. */
 RBM_API int rbm_transfer_simat_f64(const double* poses_Rt, const double* simats, double* out, int64_t n, void* stream);

@@ -529,6 +529,21 @@ int rbm_forward_dynamics_f64(const rbm_model* m, const double* q, const double* 
   return launch_forward_dynamics<double>(m, q, qd, u, dt, qdd, q_next, qd_next, n, ld, (cudaStream_t)stream);
 }
 
+int rbm_closed_loop_f64(const rbm_model* m, const double* plan_coeffs, const double* displacement, const double* pos_offset, double plan_timestep,
+                        double init_step, int64_t n_steps, const double* gain, const double* phi_sensed, double dt, double fps,
+                        double pos_residual_divisor, const double* q0, const double* qd0, double* frames, int64_t max_frames, int32_t* frame_steps,
+                        int32_t* n_frames, double* final_state, int64_t n, int64_t ld, void* stream) {
+  RBM_CHECK_BATCH("rbm_closed_loop_f64")
+  if (!plan_coeffs || !displacement || !pos_offset) return invalid("rbm_closed_loop_f64: NULL planner description");
+  if (!gain || !phi_sensed || !q0) return invalid("rbm_closed_loop_f64: NULL gain / phi_sensed / q0");
+  if (n_steps < 0 || n_steps > (int64_t)1 << 30) return invalid("rbm_closed_loop_f64: n_steps out of range");
+  if (max_frames < 0 || max_frames > (int64_t)1 << 30 || (max_frames > 0 && !frames)) return invalid("rbm_closed_loop_f64: frames / max_frames");
+  if (!(dt > 0.0) || !(plan_timestep > 0.0) || !(fps >= 0.0) || pos_residual_divisor == 0.0) return invalid("rbm_closed_loop_f64: dt, plan_timestep > 0, fps >= 0, divisor != 0");
+  if (ld < n) return invalid("rbm_closed_loop_f64: ld < n");
+  return launch_closed_loop(m, plan_coeffs, displacement, pos_offset, plan_timestep, init_step, (int)n_steps, gain, phi_sensed, dt, fps,
+                            pos_residual_divisor, q0, qd0, frames, (int)max_frames, frame_steps, n_frames, final_state, n, ld, (cudaStream_t)stream);
+}
+
 // ---- frame algebra helpers ------------------------------------------------------------------------
 #define RBM_SIMPLE_CHECK(name, cond)                       \
   if (n < 0) return invalid(name ": n < 0");               \

@@ -113,6 +113,10 @@ template <class T>
 int launch_forward_dynamics(const rbm_model* m, const T* q, const T* qd, const T* u, double dt, T* qdd, T* q_next, T* qd_next, int64_t n, int64_t ld,
                             cudaStream_t st);
 
+int launch_closed_loop(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double plan_timestep, double step0,
+                       int n_steps, const double* K, const double* phi, double dt, double fps, double div, const double* q0, const double* qd0,
+                       double* frames, int max_frames, int* frame_steps, int* n_frames, double* final_state, int64_t n, int64_t ld, cudaStream_t st);
+
 // launchers (rbm_setup.cu)
 int launch_transfer_simat(const double* poses, const double* simats, double* out, int64_t n, int pose_stride, int simat_stride, int mode, cudaStream_t st);
 int launch_transfer_imat(const double* poses, const double* imats, const double* mass, double* out, int64_t n, cudaStream_t st);

@@ -50,6 +50,15 @@ struct FastEval {
 #pragma unroll
     for (int k = 0; k < 6; ++k) tau[k] = r.tau[k];
   }
+  // twist and twist rate of the last link only (forward sweep)
+  __device__ __forceinline__ void last_twists(const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6], const T (&qdd)[6], T (&V)[6],
+                                              T (&dV)[6]) const {
+    FastResult<T> r;
+    fast_rnea_core<T, D, false>(P, P.g, q, c, s, qd, qdd, r);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { V[k] = r.v[k]; V[3 + k] = r.w[k]; dV[k] = r.a[k]; dV[3 + k] = r.l[k]; }
+  }
+  __device__ __forceinline__ const T* sensor_pose() const { return P.senR; }  // [R (9) | t (3)]
   // velocity-product term alone, C(q, qd) = ID(q, qd, 0) without gravity.  tau = M qdd + C + g, so finite differences over qd
   // at fixed (q, qdd) only need this part (and it is an exact quadratic form in qd: the centred difference has no truncation)
   __device__ __forceinline__ void id_velocity(const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6], T (&tau)[6]) const {
@@ -83,6 +92,12 @@ struct GenericEval {
                                      T (&tau)[MAXJ]) const {
     generic_rnea<T, 0>(sp, sp, nj_, q, qd, qdd, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
   }
+  __device__ __forceinline__ void last_twists(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qd)[MAXJ], const T (&qdd)[MAXJ],
+                                              T (&V)[6], T (&dV)[6]) const {
+    T tau[MAXJ];
+    generic_rnea<T, 0>(sp, sp, nj_, q, qd, qdd, tau, nullptr, nullptr, nullptr, V, dV);
+  }
+  __device__ __forceinline__ const T* sensor_pose() const { return sp + GP_SENR; }
   __device__ __forceinline__ void id_velocity(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qd)[MAXJ], T (&tau)[MAXJ]) const {
     T qdd0[MAXJ];
 #pragma unroll
@@ -483,6 +498,223 @@ __global__ void __launch_bounds__(kLinBlock) k_linearize_generic(const T* __rest
   if (s >= n) return;
   GenericEval<T> ev{sp, zero, nj};
   linearize_state<T>(ev, q, qd, u, dt, eps, centered != 0, A, B, qdd_out, s, ld);
+}
+
+
+// ---- closed-loop rollout (reference core/simulate.py:185-270), one environment per thread ---------------------------------------
+// Every step of the reference's main loop, with MuJoCo's mj_step replaced by the transition above:
+//   C(step): tgt = plan(step) (:187), tgt_ctrl = ID(tgt) (:188); act = (qpos, qvel, qacc) where qacc still belongs to the PREVIOUS
+//            forward pass (:191-194); on frame steps (`frame_count <= time * fps`, :196) log act, the sensor-frame twists of act
+//            (:202-209) and the F/T reading left by the previous forward pass (:218-221);
+//            res = [(tgt_q - qpos) / div, tgt_qd - qvel] (mj_differentiatePos with m.nu in the dt slot, :257-265);
+//            ctrl = tgt_ctrl - K res (:268)
+//   A      : forward pass at (qpos, qvel, ctrl): qacc = M^-1 (ctrl - h); F/T sensor = Newton-Euler wrench of the sensed subtree in the
+//            sensor frame = Y(V_s, dV_s) phi  (cfrc_int of body "target/" in the site frame; evaluated only when the next step logs)
+//   B      : qvel += dt qacc; qpos += dt qvel; time += dt                                  (:270)
+// started by one forward pass at the initial state with ctrl = 0 (what the controller's linearisation leaves in MjData).
+// Frame record: [act (3 nj) | V_s (6) | dV_s (6) | wrench (6)], stored value-major [frame][value][env] so that every store is coalesced.
+template <class T, class E>
+__device__ __forceinline__ void closed_loop_env(const E& ev, const PlanArg<T>& pl, const T* __restrict__ K, const T* __restrict__ phi_in, T dt, T fps,
+                                                T div, int n_steps, int max_frames, const T* __restrict__ q0, const T* __restrict__ qd0,
+                                                T* __restrict__ frames, int* __restrict__ frame_steps, int* __restrict__ n_frames,
+                                                T* __restrict__ final_state, int64_t s, int64_t ld) {
+  constexpr int MJ = E::MAXJ;
+  const int nj = ev.nj();
+  const int fv = 3 * nj + 18;
+  T q[MJ], qd[MJ], qacc[MJ], u[MJ], c[MJ], sn[MJ], zero[MJ], wrench[6], phi[10];
+#pragma unroll
+  for (int k = 0; k < MJ; ++k) {
+    const bool on = k < nj;
+    q[k] = on ? __ldg(q0 + k * ld + s) : T(0);
+    qd[k] = (on && qd0) ? __ldg(qd0 + k * ld + s) : T(0);
+    qacc[k] = u[k] = zero[k] = sn[k] = T(0);
+    c[k] = T(1);
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) phi[k] = __ldg(phi_in + k);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) wrench[k] = T(0);
+  const T* senp = ev.sensor_pose();
+  T time = T(0);
+  int frame_count = 0;
+  bool integrate = false;
+#pragma unroll 1
+  for (int it = 0; it <= n_steps; ++it) {
+    // ---- A: forward pass at (q, qd, u)
+    ev.trig(q, c, sn);
+    {
+      T M[MJ][MJ];
+#pragma unroll 1
+      for (int j = 0; j < nj; ++j) {
+        T e[MJ], col[MJ];
+#pragma unroll
+        for (int k = 0; k < MJ; ++k) e[k] = (k == j) ? T(1) : T(0);
+        ev.id_inertia(q, c, sn, e, col);
+#pragma unroll
+        for (int r = 0; r < MJ; ++r)
+#pragma unroll
+          for (int k = 0; k < MJ; ++k)
+            if (k == j) M[r][k] = col[r];
+      }
+      T h[MJ];
+      ev.id(q, c, sn, qd, zero, h);
+      cholesky<T, MJ>(M, nj);
+#pragma unroll
+      for (int k = 0; k < MJ; ++k) qacc[k] = u[k] - h[k];
+      chol_solve<T, MJ>(M, nj, qacc);
+    }
+    const T t_next = integrate ? time + dt : time;
+    if (it < n_steps && (T)frame_count <= t_next * fps) {  // the F/T reading the next frame will log
+      T V[6], dV[6], Vs[6], dVs[6], top[3][4], bot[3][9];
+      ev.last_twists(q, c, sn, qd, qacc, V, dV);
+      sensor_twists(senp, senp + 9, V, dV, Vs, dVs);
+      regressor_blocks(Vs, dVs, top, bot);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        T f = T(0), m = T(0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f += top[r][k] * phi[k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) m += bot[r][k] * phi[1 + k];
+        wrench[r] = f;
+        wrench[3 + r] = m;
+      }
+    }
+    // ---- B: integrate
+    if (integrate) {
+#pragma unroll
+      for (int k = 0; k < MJ; ++k) {
+        qd[k] = qd[k] + dt * qacc[k];
+        q[k] = q[k] + dt * qd[k];
+      }
+      time = t_next;
+    }
+    integrate = true;
+    if (it == n_steps) break;
+    // ---- C: plan, log, control law
+    T sp_, sv_, sa_, tq[MJ], tqd[MJ], tqdd[MJ], tctrl[MJ], tc[MJ], ts[MJ];
+    plan_profile(pl, (int64_t)it, sp_, sv_, sa_);
+#pragma unroll
+    for (int k = 0; k < MJ; ++k) {
+      tq[k] = pl.disp[k] * sp_ + pl.offset[k];
+      tqd[k] = pl.disp[k] * sv_;
+      tqdd[k] = pl.disp[k] * sa_;
+      tc[k] = T(1);
+      ts[k] = T(0);
+    }
+    ev.trig(tq, tc, ts);
+    ev.id(tq, tc, ts, tqd, tqdd, tctrl);
+    if ((T)frame_count <= time * fps) {
+      if (frame_count < max_frames) {
+        T V[6], dV[6], Vs[6], dVs[6];
+        ev.trig(q, c, sn);
+        ev.last_twists(q, c, sn, qd, qacc, V, dV);
+        sensor_twists(senp, senp + 9, V, dV, Vs, dVs);
+        T* dst = frames + ((int64_t)frame_count * fv) * ld + s;
+#pragma unroll
+        for (int k = 0; k < MJ; ++k) {
+          if (k < nj) {
+            dst[(int64_t)k * ld] = q[k];
+            dst[(int64_t)(nj + k) * ld] = qd[k];
+            dst[(int64_t)(2 * nj + k) * ld] = qacc[k];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          dst[(int64_t)(3 * nj + k) * ld] = Vs[k];
+          dst[(int64_t)(3 * nj + 6 + k) * ld] = dVs[k];
+          dst[(int64_t)(3 * nj + 12 + k) * ld] = wrench[k];
+        }
+        if (s == 0 && frame_steps) frame_steps[frame_count] = it;
+      }
+      ++frame_count;
+    }
+#pragma unroll
+    for (int r = 0; r < MJ; ++r) {
+      if (r < nj) {
+        T v = tctrl[r];
+        for (int k = 0; k < nj; ++k) {
+          v -= __ldg(K + r * 2 * nj + k) * ((tq[k] - q[k]) / div);
+          v -= __ldg(K + r * 2 * nj + nj + k) * (tqd[k] - qd[k]);
+        }
+        u[r] = v;
+      }
+    }
+  }
+  if (s == 0 && n_frames) *n_frames = frame_count;
+  if (final_state) {
+#pragma unroll
+    for (int k = 0; k < MJ; ++k) {
+      if (k < nj) {
+        final_state[(int64_t)k * ld + s] = q[k];
+        final_state[(int64_t)(nj + k) * ld + s] = qd[k];
+        final_state[(int64_t)(2 * nj + k) * ld + s] = qacc[k];
+      }
+    }
+  }
+}
+
+constexpr int kLoopBlock = 64;  // few environments per block: a rollout is one long serial chain per thread, so spread envs over the SMs
+
+template <class T, class D>
+__global__ void __launch_bounds__(kLoopBlock) k_closed_loop_fast(const __grid_constant__ FastParams<T> P, const __grid_constant__ PlanArg<T> pl,
+                                                                 const T* __restrict__ K, const T* __restrict__ phi, T dt, T fps, T div, int n_steps,
+                                                                 int max_frames, const T* __restrict__ q0, const T* __restrict__ qd0, T* __restrict__ frames,
+                                                                 int* __restrict__ frame_steps, int* __restrict__ n_frames, T* __restrict__ final_state,
+                                                                 int64_t n, int64_t ld) {
+  const int64_t s = (int64_t)blockIdx.x * kLoopBlock + threadIdx.x;
+  if (s >= n) return;
+  FastEval<T, D> ev{P};
+  closed_loop_env<T>(ev, pl, K, phi, dt, fps, div, n_steps, max_frames, q0, qd0, frames, frame_steps, n_frames, final_state, s, ld);
+}
+
+template <class T>
+__global__ void __launch_bounds__(kLoopBlock) k_closed_loop_generic(const T* __restrict__ gp, int nj, int nparams, const __grid_constant__ PlanArg<T> pl,
+                                                                    const T* __restrict__ K, const T* __restrict__ phi, T dt, T fps, T div, int n_steps,
+                                                                    int max_frames, const T* __restrict__ q0, const T* __restrict__ qd0,
+                                                                    T* __restrict__ frames, int* __restrict__ frame_steps, int* __restrict__ n_frames,
+                                                                    T* __restrict__ final_state, int64_t n, int64_t ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sp = reinterpret_cast<T*>(smem_raw);
+  T* zero = sp + nparams;
+  for (int i = threadIdx.x; i < nparams; i += blockDim.x) sp[i] = gp[i];
+  for (int i = threadIdx.x; i < 18; i += blockDim.x) zero[i] = T(0);
+  __syncthreads();
+  const int64_t s = (int64_t)blockIdx.x * kLoopBlock + threadIdx.x;
+  if (s >= n) return;
+  GenericEval<T> ev{sp, zero, nj};
+  closed_loop_env<T>(ev, pl, K, phi, dt, fps, div, n_steps, max_frames, q0, qd0, frames, frame_steps, n_frames, final_state, s, ld);
+}
+
+int launch_closed_loop(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double plan_timestep, double step0,
+                       int n_steps, const double* K, const double* phi, double dt, double fps, double div, const double* q0, const double* qd0,
+                       double* frames, int max_frames, int* frame_steps, int* n_frames, double* final_state, int64_t n, int64_t ld, cudaStream_t st) {
+  if (n == 0) return RBM_OK;
+  using T = double;
+  PlanArg<T> pl;
+  for (int k = 0; k < 6; ++k) pl.coeffs[k] = coeffs[k];
+  for (int k = 0; k < RBM_MAX_JOINTS; ++k) {
+    pl.disp[k] = k < m->nj ? disp[k] : 0.0;
+    pl.offset[k] = k < m->nj ? offset[k] : 0.0;
+  }
+  pl.inv_dt = 1.0 / plan_timestep;
+  pl.inv_dt2 = 1.0 / (plan_timestep * plan_timestep);
+  pl.step0 = step0;
+  pl.stride = 1.0;
+  const unsigned grid = (unsigned)((n + kLoopBlock - 1) / kLoopBlock);
+  if (m->path == PATH_SEQ_ISO) {
+    k_closed_loop_fast<T, SeqIso><<<grid, kLoopBlock, 0, st>>>(ModelView<T>::fast(m), pl, K, phi, dt, fps, div, n_steps, max_frames, q0, qd0, frames,
+                                                              frame_steps, n_frames, final_state, n, ld);
+  } else if (m->path == PATH_SEQ_RIGID) {
+    k_closed_loop_fast<T, SeqRigid><<<grid, kLoopBlock, 0, st>>>(ModelView<T>::fast(m), pl, K, phi, dt, fps, div, n_steps, max_frames, q0, qd0, frames,
+                                                                frame_steps, n_frames, final_state, n, ld);
+  } else {
+    const int np = generic_param_count(m->nj);
+    k_closed_loop_generic<T><<<grid, kLoopBlock, sizeof(T) * (np + 18), st>>>(ModelView<T>::generic(m), m->nj, np, pl, K, phi, dt, fps, div, n_steps,
+                                                                             max_frames, q0, qd0, frames, frame_steps, n_frames, final_state, n, ld);
+  }
+  RBM_CUDA_TRY(cudaGetLastError());
+  return RBM_OK;
 }
 
 template <class T>

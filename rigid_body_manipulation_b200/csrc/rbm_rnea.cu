@@ -308,25 +308,7 @@ __global__ void __launch_bounds__(kBlock) k_rnea_generic_aos(const T* __restrict
 // ---------------------------------------------------------------------------------------------
 // The profile is always evaluated in double, also in fp32 mode: in the power basis of the integer step variable
 // (k^5 up to ~1e16 against coefficients down to ~1e-16) single precision would lose every digit to cancellation.
-template <class T>
-struct PlanArg {
-  double coeffs[6];          // s(k) = c0 k^5 + c1 k^4 + ... + c5   (normalised profile in the step variable k)
-  double inv_dt, inv_dt2;    // 1 / timestep, 1 / timestep^2
-  double step0, stride;      // sample s evaluates step k = step0 + s * stride
-  T disp[RBM_MAX_JOINTS];    // displacement per joint
-  T offset[RBM_MAX_JOINTS];  // pos_offset per joint
-};
-
-template <class T>
-__device__ __forceinline__ void plan_profile(const PlanArg<T>& pl, int64_t s, T& sp, T& sv, T& sa) {
-  const double k = pl.step0 + (double)s * pl.stride;
-  const double k2 = k * k, k3 = k2 * k, k4 = k3 * k, k5 = k4 * k;
-  const double* c = pl.coeffs;
-  sp = (T)(c[0] * k5 + c[1] * k4 + c[2] * k3 + c[3] * k2 + c[4] * k + c[5]);                                  // :120,125
-  sv = (T)((5.0 * c[0] * k4 + 4.0 * c[1] * k3 + 3.0 * c[2] * k2 + 2.0 * c[3] * k + c[4]) * pl.inv_dt);        // :121,126
-  sa = (T)((20.0 * c[0] * k3 + 12.0 * c[1] * k2 + 6.0 * c[2] * k + 2.0 * c[3]) * pl.inv_dt2);                 // :122-123,127
-}
-
+// PlanArg / plan_profile live in rbm_rnea.cuh (shared with the closed-loop rollout of rbm_linearize.cu)
 template <class T, class D>
 __global__ void __launch_bounds__(kBlock) k_rnea_planned_fast(const __grid_constant__ FastParams<T> P, const __grid_constant__ PlanArg<T> pl,
                                                               T* __restrict__ tau, T* __restrict__ traj /* [3*6][ld] or null */, int64_t n, int64_t ld) {

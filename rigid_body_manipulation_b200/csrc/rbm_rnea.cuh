@@ -448,4 +448,26 @@ RBM_HD void regressor_blocks(const T* V, const T* dV, T (&top)[3][4], T (&bot)[3
   bot[2][3] = -xy;  bot[2][4] = xy;   bot[2][5] = lz;   bot[2][6] = xx - yy; bot[2][7] = ly + zx; bot[2][8] = lx - yz;
 }
 
+// ---- planner-driven inputs (planners/joint_position_planner.py:86-131): the quintic profile is evaluated in double in the step
+// variable k
+template <class T>
+struct PlanArg {
+  double coeffs[6];          // s(k) = c0 k^5 + c1 k^4 + ... + c5   (normalised profile in the step variable k)
+  double inv_dt, inv_dt2;    // 1 / timestep, 1 / timestep^2
+  double step0, stride;      // sample s evaluates step k = step0 + s * stride
+  T disp[RBM_MAX_JOINTS];    // displacement per joint
+  T offset[RBM_MAX_JOINTS];  // pos_offset per joint
+};
+
+template <class T>
+RBM_HD void plan_profile(const PlanArg<T>& pl, int64_t s, T& sp, T& sv, T& sa) {
+  const double k = pl.step0 + (double)s * pl.stride;
+  const double k2 = k * k, k3 = k2 * k, k4 = k3 * k, k5 = k4 * k;
+  const double* c = pl.coeffs;
+  sp = (T)(c[0] * k5 + c[1] * k4 + c[2] * k3 + c[3] * k2 + c[4] * k + c[5]);                                  // :120,125
+  sv = (T)((5.0 * c[0] * k4 + 4.0 * c[1] * k3 + 3.0 * c[2] * k2 + 2.0 * c[3] * k + c[4]) * pl.inv_dt);        // :121,126
+  sa = (T)((20.0 * c[0] * k3 + 12.0 * c[1] * k2 + 6.0 * c[2] * k + 2.0 * c[3]) * pl.inv_dt2);                 // :122-123,127
+}
+
+
 }  // namespace rbm

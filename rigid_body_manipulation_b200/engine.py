@@ -333,6 +333,44 @@ class Model:
         return qn, qdn
 
 
+    # ---- closed-loop rollout -----------------------------------------------------------------------------
+    def closed_loop(self, plan, gain, phi_sensed, q0, qd0=None, dt=None, fps=50.0, pos_residual_divisor=None, max_frames=None, want_final=True):
+        """The reference's main loop (core/simulate.py:185-270) for n environments in ONE launch (one environment per thread).
+        plan: planner.QuinticPlan;  gain: (nj, 2 nj);  phi_sensed: the 10 inertial parameters of the body hanging off the F/T sensor, in
+        the sensor frame;  q0 [, qd0]: CUDA (nj, n) float64 initial states.  Returns a dict of device tensors:
+          frames (F, 3 nj + 18, n) = [act (3 nj) | V_s | dV_s | wrench] per logged frame, frame_steps (F,) int32, final (3 nj, n)."""
+        self._check_dev(q0, qd0)
+        if q0.dtype != torch.float64 or q0.dim() != 2 or q0.shape[0] != self.nj or (qd0 is not None and (qd0.shape != q0.shape or qd0.dtype != q0.dtype)):
+            raise ValueError(f"q0, qd0 must be float64 with shape ({self.nj}, n)")
+        if len(plan.displacement) != self.nj or len(plan.pos_offset) != self.nj:
+            raise ValueError(f"plan must have {self.nj} joints")
+        n, nj = q0.shape[1], self.nj
+        dt = float(plan.timestep if dt is None else dt)
+        div = float(nj if pos_residual_divisor is None else pos_residual_divisor)  # the reference passes m.nu as mj_differentiatePos' dt
+        K = torch.as_tensor(np.ascontiguousarray(gain, dtype=np.float64), device=self.device)
+        if K.shape != (nj, 2 * nj):
+            raise ValueError(f"gain must have shape ({nj}, {2 * nj})")
+        ph = torch.as_tensor(np.ascontiguousarray(phi_sensed, dtype=np.float64), device=self.device)
+        if ph.shape != (10,):
+            raise ValueError("phi_sensed must hold the 10 inertial parameters")
+        if max_frames is None:
+            max_frames = int(np.ceil(plan.n_steps * dt * fps)) + 2
+        frames = torch.zeros((max_frames, 3 * nj + 18, n), dtype=torch.float64, device=self.device)
+        fsteps = torch.full((max_frames,), -1, dtype=torch.int32, device=self.device)
+        nfr = torch.zeros(1, dtype=torch.int32, device=self.device)
+        final = torch.empty((3 * nj, n), dtype=torch.float64, device=self.device) if want_final else None
+        co = np.ascontiguousarray(plan.coeffs, dtype=np.float64)
+        di = np.ascontiguousarray(plan.displacement, dtype=np.float64)
+        of = np.ascontiguousarray(plan.pos_offset, dtype=np.float64)
+        with torch.cuda.device(self.device):
+            rc = self._lib.rbm_closed_loop_f64(self._h, _ptr(co), _ptr(di), _ptr(of), float(plan.timestep), float(plan.init_step), int(plan.n_steps),
+                                               _ptr(K), _ptr(ph), dt, float(fps), div, _ptr(q0), _ptr(qd0), _ptr(frames), int(max_frames), _ptr(fsteps),
+                                               _ptr(nfr), _ptr(final), n, n, self._stream())
+        _lib.check(rc, "rbm_closed_loop")
+        nf = min(int(nfr.item()), max_frames)
+        return dict(frames=frames[:nf], frame_steps=fsteps[:nf], final=final, n_frames_total=int(nfr.item()))
+
+
 # ---- model-free batched helpers (device tensors in, device tensors out) ------------------------------------
 def _dev64(x, shape_tail):
     t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float64))

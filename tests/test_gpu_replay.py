@@ -1,0 +1,95 @@
+"""Closed-loop replay (reference core/simulate.py:185-290): the one-launch GPU rollout against the literal CPU
+restatement of the loop (oracle/replay_oracle.py).  Both sides replace MuJoCo by the same published semantics, so this pins the
+kernel to the restatement, not to a MuJoCo run (stated in DESIGN.md)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_util import model_from_golden
+from oracle import replay_oracle as ro
+from rigid_body_manipulation_b200 import identification as idn
+from rigid_body_manipulation_b200 import model as pm
+from rigid_body_manipulation_b200 import planner, replay
+
+pytestmark = pytest.mark.gpu
+
+INPUT_GAIN = [10.0, 10.0, 10.0, 1e4, 1e4, 1e4]  # configurations/base.yaml controller.input_gain
+DISP = [0.2, 1.4, 0.6, np.pi, 0.0, 18.8495559215]  # configurations/base.yaml planner.displacements
+
+
+def _setup(target="hammer", n_steps=1500):
+    c = pm.load_packaged("sequential", target)
+    consts = dict(hposes_Rt=c.hposes_Rt, simats=c.simats, uscrews=c.uscrews, twist_0=c.twist_0, dtwist_0=c.dtwist_0)
+    G_s = ro.sensor_inertia(c.simat_object_llj, c.pose_sen_Rt)
+    plan = planner.QuinticPlan(DISP, c.key_qpos, 0.002, n_steps)
+    return c, consts, G_s, plan
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_rollout_matches_the_literal_loop(force_generic):
+    from rigid_body_manipulation_b200.engine import Model
+
+    n_steps = 400 if force_generic else 1500
+    c, consts, G_s, plan = _setup(n_steps=n_steps)
+    m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, pose_sen_llj=c.pose_sen_Rt, force_generic=force_generic)
+    K = replay.lqr_gain(m, c.key_qpos, INPUT_GAIN)
+    Kr = ro.lqr_gain(consts, c.key_qpos, np.zeros(6), INPUT_GAIN)
+    assert np.abs(K - Kr).max() < 1e-4 * np.abs(Kr).max()
+    phi = ro.inertia_to_phi(G_s)
+    # environment 0 starts at the keyframe, environment 1 from a perturbed state
+    q0 = np.stack([c.key_qpos, c.key_qpos + [0.01, -0.02, 0.015, 0.05, -0.04, 0.03]], axis=1)
+    qd0 = np.stack([np.zeros(6), [0.02, 0.01, -0.03, 0.1, -0.2, 0.05]], axis=1)
+    log = replay.closed_loop_replay(m, plan, Kr, phi, torch.as_tensor(q0, device="cuda"), torch.as_tensor(qd0, device="cuda"))
+    steps = log.frame_steps.cpu().numpy()
+    plan_traj = plan.trajectory()
+    for e in range(2):
+        ref = ro.closed_loop_replay(consts, c.pose_sen_Rt, G_s, plan_traj, Kr, q0[:, e], qd0[:, e])
+        assert np.array_equal(steps, ref["step"])
+        np.testing.assert_allclose(log.time, ref["time"], rtol=0, atol=0)
+        got = log.env(e)
+        for name, key in (("trajectory", "act"), ("twists_sen", "twist_sen"), ("dtwists_sen", "dtwist_sen"), ("fts_sen", "wrench")):
+            scale = np.abs(ref[key]).max()
+            assert np.abs(got[name] - ref[key]).max() < 1e-9 * scale, (e, name, np.abs(got[name] - ref[key]).max() / scale)
+        fin = log.final[..., e].cpu().numpy()
+        assert np.abs(fin[0] - ref["q_final"]).max() < 1e-10 and np.abs(fin[1] - ref["qd_final"]).max() < 1e-10
+
+
+def test_config1_replay_identifies_the_object():
+    """configs[0] end to end: keyframe start, base.yaml plan and gains, 150 logged frames, noise-free and noisy identification."""
+    from rigid_body_manipulation_b200.engine import Model
+
+    c, consts, G_s, plan = _setup("hammer")
+    m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, pose_sen_llj=c.pose_sen_Rt)
+    K = replay.lqr_gain(m, c.key_qpos, INPUT_GAIN)
+    phi = idn.sensor_frame_params(c.target, c.pose_sen_obj_Rt)
+    log = replay.closed_loop_replay(m, plan, K, phi, n_envs=3)
+    assert log.frame_steps.shape[0] == 150 and int(log.frame_steps[0]) == 0 and int(log.frame_steps[1]) == 10
+    # tracking: the feed-forward carries the motion (the reference's feedback is weak and enters with the residual's sign)
+    tgt = plan.trajectory()[log.frame_steps.cpu().numpy()]
+    err = np.abs(log.trajectory[:, 0, :, 0].cpu().numpy() - tgt[:, 0])
+    assert err[:, :3].max() < 1e-3 and err[:, 3:].max() < 0.05
+    # identical environments give identical logs
+    assert torch.equal(log.fts_sen[..., 0], log.fts_sen[..., 2])
+    clean = replay.identify(m, log, 0, perturb=False)
+    assert abs(clean.phi[0] - phi[0]) < 1e-3 * phi[0]            # mass
+    assert np.abs(clean.phi[1:4] - phi[1:4]).max() < 2e-3        # first moments (the one-step lag between qacc and qpos biases them)
+    noisy = replay.identify(m, log, 0, perturb=True)
+    assert abs(noisy.phi[0] - phi[0]) < 0.05 * phi[0]
+    assert idn.score(clean.phi, phi, c.target.aabb_scale) < idn.score(noisy.phi, phi, c.target.aabb_scale)
+
+
+def test_argument_checks():
+    from rigid_body_manipulation_b200.engine import Model
+
+    c, _, _, plan = _setup(n_steps=10)
+    m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, pose_sen_llj=c.pose_sen_Rt)
+    q0 = torch.zeros((6, 4), dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):
+        m.closed_loop(plan, np.zeros((6, 6)), np.zeros(10), q0)
+    with pytest.raises(ValueError):
+        m.closed_loop(plan, np.zeros((6, 12)), np.zeros(9), q0)
+    with pytest.raises(ValueError):
+        m.closed_loop(plan, np.zeros((6, 12)), np.zeros(10), q0, pos_residual_divisor=0.0)
+    out = m.closed_loop(plan, np.zeros((6, 12)), np.zeros(10), q0, fps=0.0)   # fps 0: only the very first frame
+    assert out["frames"].shape[0] == 1
