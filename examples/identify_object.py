@@ -60,6 +60,14 @@ def main():
     for k, name in enumerate(idn.PARAM_LABELS):
         print(f"{name:>12} {phi_true[k]:22.6e}" + "".join(f" {est.phi[k]:14.6e}" for est in ests))
     print(f"{'score':>12} {'':>22}" + "".join(f" {idn.score(est.phi, phi_true, c.target.aabb_scale):14.3e}" for est in ests))
+    if a.envs > 1:  # every environment at once: one grouped Gram launch + the host solves
+        t0 = time.perf_counter()
+        all_ests = replay.identify_all(m, log, perturb=True, seed=0)
+        t_id = time.perf_counter() - t0
+        masses = np.array([e.phi[0] for e in all_ests])
+        scores = np.array([idn.score(e.phi, phi_true, c.target.aabb_scale) for e in all_ests])
+        print(f"\nall {a.envs} environments identified in {t_id * 1e3:.1f} ms: mass {masses.mean():.5f} +- {masses.std():.5f} kg "
+              f"(truth {phi_true[0]:.5f}), median score {np.median(scores):.3e}")
     clean = replay.identify(m, log, 0, perturb=False)
     print(f"\nnoise-free estimate, env 0: score {idn.score(clean.phi, phi_true, c.target.aabb_scale):.3e}, rms residual {clean.rms_residual:.3e} N")
     print("(the reference scores against the object-frame CAD numbers, main.py:79-82; in that frame the score would be "

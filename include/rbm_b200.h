@@ -166,6 +166,13 @@ RBM_API int rbm_regressor_gram_f64(const rbm_model* m, const double* q, const do
 RBM_API int rbm_regressor_gram_f32(const rbm_model* m, const float* q, const float* qd, const float* qdd, const float* f, double* gram_pack,
                            void* workspace, size_t workspace_bytes, int64_t n, int64_t ld, void* stream);
 
+/* One Gram pack per GROUP (environment / object) for logs stored frame-major: sample `fr` of group g has its row k at
+ *   x[fr * frame_stride + k * ld + g]  (x = q, qd, qdd: nj rows)   and   f[fr * f_frame_stride + k * ld + g]  (6 rows)
+ * e.g. the frame log of rbm_closed_loop_f64 (q = frames, qd = frames + nj ld, qdd = frames + 2 nj ld, f = frames + (3 nj + 12) ld,
+ * frame_stride = f_frame_stride = (3 nj + 18) ld), or the same trajectories with a separately stored (noisy) wrench array.  One group per thread, no workspace;  gram_packs: [112][ld_out], column g = the pack of group g. */
+RBM_API int rbm_regressor_gram_grouped_f64(const rbm_model* m, const double* q, const double* qd, const double* qdd, const double* f, int64_t frame_stride,
+                                   int64_t f_frame_stride, int64_t n_frames, double* gram_packs, int64_t n_groups, int64_t ld, int64_t ld_out, void* stream);
+
 /* ---- the one collective: all-reduce of the Gram pack over NCCL ------------------------------------------------
  * Each rank accumulates the pack of its shard (rbm_regressor_gram_*), then rbm_allreduce_gram sums the 112 doubles in place
  * across ranks on `stream` (enqueue it right behind the Gram call: no host synchronisation is needed in between).

@@ -77,6 +77,7 @@ SIGNATURES = {
     "rbm_allreduce_gram_n": (C.c_int, [_vp, _vp, _i64, _vp]),
     "rbm_linearize_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp, _i64, _i64, _vp]),
     "rbm_forward_dynamics_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "rbm_regressor_gram_grouped_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp]),
     "rbm_closed_loop_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _i64, _vp, _vp, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp, _i64,
                                       _vp, _vp, _vp, _i64, _i64, _vp]),
     "rbm_transfer_simat_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),

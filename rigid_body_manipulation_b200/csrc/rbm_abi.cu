@@ -509,6 +509,16 @@ int rbm_regressor_gram_f32(const rbm_model* m, const float* q, const float* qd, 
   return regressor_gram<float>("rbm_regressor_gram_f32", m, q, qd, qdd, f, gram_pack, workspace, workspace_bytes, n, ld, stream);
 }
 
+int rbm_regressor_gram_grouped_f64(const rbm_model* m, const double* q, const double* qd, const double* qdd, const double* f, int64_t frame_stride,
+                                   int64_t f_frame_stride, int64_t n_frames, double* gram_packs, int64_t n_groups, int64_t ld, int64_t ld_out, void* stream) {
+  const int64_t n = n_groups;
+  RBM_CHECK_BATCH("rbm_regressor_gram_grouped_f64")
+  if (!q || !qd || !qdd || !f || !gram_packs) return invalid("rbm_regressor_gram_grouped_f64: NULL pointer");
+  if (n_frames < 0 || frame_stride < 0 || f_frame_stride < 0) return invalid("rbm_regressor_gram_grouped_f64: n_frames / frame_stride < 0");
+  if (ld < n_groups || ld_out < n_groups) return invalid("rbm_regressor_gram_grouped_f64: ld / ld_out < n_groups");
+  return launch_regressor_gram_grouped<double>(m, q, qd, qdd, f, frame_stride, f_frame_stride, n_frames, gram_packs, n_groups, ld, ld_out, (cudaStream_t)stream);
+}
+
 int rbm_linearize_f64(const rbm_model* m, const double* q, const double* qd, const double* u, double dt, double eps, int centered, double* A,
                       double* B, double* qdd, int64_t n, int64_t ld, void* stream) {
   RBM_CHECK_BATCH("rbm_linearize_f64")

@@ -103,6 +103,9 @@ int launch_regressor_from_traj(const rbm_model* m, const T* q, const T* qd, cons
 template <class T>
 int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* qdd, const T* f, double* pack, double* partials, int64_t n, int64_t ld,
                           cudaStream_t st);
+template <class T>
+int launch_regressor_gram_grouped(const rbm_model* m, const T* q, const T* qd, const T* qdd, const T* f, int64_t frame_stride, int64_t f_frame_stride,
+                                  int64_t n_frames, double* packs, int64_t n_groups, int64_t ld, int64_t ld_out, cudaStream_t st);
 
 // launcher (rbm_linearize.cu)
 template <class T>

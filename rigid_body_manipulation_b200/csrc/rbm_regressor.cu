@@ -413,6 +413,58 @@ __global__ void __launch_bounds__(128) k_gram_finalize(const double* __restrict_
   }
 }
 
+// ---- grouped variant: one Gram pack per GROUP (environment / object), one group per thread ----------------------------------
+// For logs laid out [frame][row][group] (the closed-loop rollout's frame log, rbm_linearize.cu): thread g walks its n_frames samples,
+// keeps the 70 accumulators in registers and writes its own 112-double pack, value-major [112][ld_out] (coalesced).
+template <class T, int PATH>
+__global__ void __launch_bounds__(kRowsBlock) k_regressor_gram_grouped(const __grid_constant__ FastParams<T> P, const T* __restrict__ gp, int nj, int nparams,
+                                                                       const T* __restrict__ q, const T* __restrict__ qd, const T* __restrict__ qdd,
+                                                                       const T* __restrict__ f, int64_t frame_stride, int64_t f_frame_stride,
+                                                                       int64_t n_frames, double* __restrict__ packs, int64_t n_groups, int64_t ld, int64_t ld_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sp = reinterpret_cast<T*>(smem_raw);
+  if constexpr (PATH == PATH_GENERIC) {
+    for (int i = threadIdx.x; i < nparams; i += blockDim.x) sp[i] = gp[i];
+    __syncthreads();
+  }
+  const int64_t g = (int64_t)blockIdx.x * kRowsBlock + threadIdx.x;
+  if (g >= n_groups) return;
+  const T* R = sensor_R(P, sp, PATH == PATH_GENERIC);
+  double acc[kAcc];
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+#pragma unroll 1
+  for (int64_t fr = 0; fr < n_frames; ++fr) {
+    const int64_t off = fr * frame_stride;
+    T V[6], dV[6], Vs[6], dVs[6], fs[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) fs[k] = __ldg(f + fr * f_frame_stride + k * ld + g);
+    last_link_twists<T, PATH>(P, sp, nj, q + off, qd + off, qdd + off, g, ld, V, dV);
+    sensor_twists(R, R + 9, V, dV, Vs, dVs);
+    T top[3][4], bot[3][9];
+    regressor_blocks(Vs, dVs, top, bot);
+    gram_accumulate(acc, top, bot, fs);
+  }
+  auto tri = [](int n_, int i, int j) { if (i > j) { int t = i; i = j; j = t; } return i * n_ - i * (i - 1) / 2 + (j - i); };
+  double* out = packs + g;
+#pragma unroll
+  for (int a = 0; a < 10; ++a) {
+#pragma unroll
+    for (int b = 0; b < 10; ++b) {
+      double v = 0.0;
+      if (a <= 3 && b <= 3) v += acc[tri(5, a, b)];
+      if (a >= 1 && b >= 1) v += acc[kTop + tri(10, a - 1, b - 1)];
+      out[(int64_t)(a * 10 + b) * ld_out] = v;
+    }
+    double v = 0.0;
+    if (a <= 3) v += acc[tri(5, a, 4)];
+    if (a >= 1) v += acc[kTop + tri(10, a - 1, 9)];
+    out[(int64_t)(100 + a) * ld_out] = v;
+  }
+  out[(int64_t)110 * ld_out] = acc[tri(5, 4, 4)] + acc[kTop + tri(10, 9, 9)];
+  out[(int64_t)111 * ld_out] = (double)n_frames;
+}
+
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
@@ -465,6 +517,28 @@ int launch_regressor_from_traj(const rbm_model* m, const T* q, const T* qd, cons
   RBM_CUDA_TRY(cudaGetLastError());
   return RBM_OK;
 }
+
+template <class T>
+int launch_regressor_gram_grouped(const rbm_model* m, const T* q, const T* qd, const T* qdd, const T* f, int64_t frame_stride, int64_t f_frame_stride,
+                                  int64_t n_frames,
+                                  double* packs, int64_t n_groups, int64_t ld, int64_t ld_out, cudaStream_t st) {
+  if (n_groups == 0) return RBM_OK;
+  const unsigned grid = (unsigned)((n_groups + kRowsBlock - 1) / kRowsBlock);
+  const int np = generic_param_count(m->nj);
+  const FastParams<T>& P = ModelView<T>::fast(m);
+  const T* gp = ModelView<T>::generic(m);
+  if (m->path == PATH_SEQ_ISO)
+    k_regressor_gram_grouped<T, PATH_SEQ_ISO><<<grid, kRowsBlock, 0, st>>>(P, gp, m->nj, np, q, qd, qdd, f, frame_stride, f_frame_stride, n_frames, packs, n_groups, ld, ld_out);
+  else if (m->path == PATH_SEQ_RIGID)
+    k_regressor_gram_grouped<T, PATH_SEQ_RIGID><<<grid, kRowsBlock, 0, st>>>(P, gp, m->nj, np, q, qd, qdd, f, frame_stride, f_frame_stride, n_frames, packs, n_groups, ld, ld_out);
+  else
+    k_regressor_gram_grouped<T, PATH_GENERIC><<<grid, kRowsBlock, sizeof(T) * np, st>>>(P, gp, m->nj, np, q, qd, qdd, f, frame_stride, f_frame_stride, n_frames, packs, n_groups,
+                                                                                      ld, ld_out);
+  RBM_CUDA_TRY(cudaGetLastError());
+  return RBM_OK;
+}
+template int launch_regressor_gram_grouped<double>(const rbm_model*, const double*, const double*, const double*, const double*, int64_t, int64_t, int64_t, double*,
+                                                   int64_t, int64_t, int64_t, cudaStream_t);
 
 template <class T>
 int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* qdd, const T* f, double* pack, double* partials, int64_t n, int64_t ld,

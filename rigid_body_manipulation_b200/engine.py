@@ -288,6 +288,26 @@ class Model:
         _lib.check(rc, "rbm_regressor_gram")
         return pack
 
+    def regressor_gram_grouped(self, q, qd, qdd, f):
+        """One Gram pack per group for frame-major logs: q, qd, qdd (F, nj, n) and f (F, 6, n), float64 CUDA tensors.  Strided VIEWS of
+        a log tensor are consumed in place: q, qd, qdd must share their frame stride, all four the row stride, and the group axis must
+        be dense.  Returns packs (n, 112) (a transposed view of the kernel's [112][n] output)."""
+        F, nj, n = q.shape
+        ts = (q, qd, qdd, f)
+        if any((not t.is_cuda) or t.device != self.device for t in ts):
+            raise ValueError(f"tensors must live on {self.device}; there is no CPU path")
+        if nj != self.nj or qd.shape != q.shape or qdd.shape != q.shape or f.shape != (F, 6, n) or any(t.dtype != torch.float64 for t in ts):
+            raise ValueError(f"q, qd, qdd must be float64 (F, {self.nj}, n) and f (F, 6, n)")
+        st = q.stride()
+        if any(t.stride(2) != 1 or t.stride(1) != st[1] for t in ts) or (F > 1 and any(t.stride(0) != st[0] for t in (qd, qdd))):
+            raise ValueError("q, qd, qdd must share their frame stride, all four arrays the row stride, with a dense group axis")
+        packs = torch.empty((112, n), dtype=torch.float64, device=q.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.rbm_regressor_gram_grouped_f64(self._h, _ptr(q), _ptr(qd), _ptr(qdd), _ptr(f), int(st[0]) if F > 1 else 0,
+                                                          int(f.stride(0)) if F > 1 else 0, F, _ptr(packs), n, int(st[1]), n, self._stream())
+        _lib.check(rc, "rbm_regressor_gram_grouped")
+        return packs.t()
+
     # ---- LQR linearisation -----------------------------------------------------------------------------
     def linearize(self, q, qd, u=None, dt=0.002, eps=1e-8, centered=True, want_qdd=False):
         """States (q, qd) (nj, n) [+ ctrl u (nj, n)] -> A (n, 2nj, 2nj), B (n, 2nj, nj) as element-major VIEWS

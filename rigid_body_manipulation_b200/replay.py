@@ -89,3 +89,25 @@ def identify(model, log: ReplayLog, env: int = 0, perturb: bool = True, error_ra
     q, qd, qdd = (tr[:, k].t().contiguous() for k in range(3))
     ft = torch.as_tensor(np.ascontiguousarray(f.T), device=model.device)
     return idn.solve(model.regressor_gram(q, qd, qdd, ft))
+
+
+def perturb_wrench_device(fts: torch.Tensor, error_rate: float = 0.05, seed: int = 0) -> torch.Tensor:
+    """core/simulate.py:281-290 for every environment at once: fts (F, 6, n) on the device; sigma per environment = error_rate x the
+    largest force (resp. torque) norm over its frames.  Same noise MODEL as identification.perturb_wrench, torch's generator instead of
+    numpy's (so the draws differ from the reference's; use `identify` for the reference's exact stream)."""
+    g = torch.Generator(device=fts.device).manual_seed(seed)
+    out = fts.clone()
+    fs_std = error_rate * fts[:, :3].norm(dim=1).amax(dim=0)   # (n,)
+    ts_std = error_rate * fts[:, 3:].norm(dim=1).amax(dim=0)
+    noise = torch.randn(fts.shape, generator=g, device=fts.device, dtype=fts.dtype)
+    out[:, :3] += fs_std * noise[:, :3]
+    out[:, 3:] += ts_std * noise[:, 3:]
+    return out
+
+
+def identify_all(model, log: ReplayLog, perturb: bool = True, error_rate: float = 0.05, seed: int = 0) -> list:
+    """Identification of EVERY environment of a log: one grouped Gram launch (one environment per thread), then the 10x10 solves."""
+    f = perturb_wrench_device(log.fts_sen, error_rate, seed) if perturb else log.fts_sen
+    tr = log.trajectory
+    packs = model.regressor_gram_grouped(tr[:, 0], tr[:, 1], tr[:, 2], f.contiguous() if perturb else f)
+    return idn.solve_many(packs)

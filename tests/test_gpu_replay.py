@@ -93,3 +93,34 @@ def test_argument_checks():
         m.closed_loop(plan, np.zeros((6, 12)), np.zeros(10), q0, pos_residual_divisor=0.0)
     out = m.closed_loop(plan, np.zeros((6, 12)), np.zeros(10), q0, fps=0.0)   # fps 0: only the very first frame
     assert out["frames"].shape[0] == 1
+
+
+def test_grouped_gram_equals_per_environment_grams():
+    from rigid_body_manipulation_b200.engine import Model
+
+    c, consts, G_s, plan = _setup("uniform_gearbox", n_steps=500)
+    phi = idn.sensor_frame_params(c.target, c.pose_sen_obj_Rt)
+    for force_generic in (False, True):
+        m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, pose_sen_llj=c.pose_sen_Rt, force_generic=force_generic)
+        K = replay.lqr_gain(m, c.key_qpos, INPUT_GAIN)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        q0 = torch.as_tensor(c.key_qpos, device="cuda").reshape(6, 1) + 0.01 * torch.randn((6, 37), generator=g, device="cuda", dtype=torch.float64)
+        log = replay.closed_loop_replay(m, plan, -K, phi, q0.contiguous(), pos_residual_divisor=1.0)   # stabilising sign: see examples/
+        ests = replay.identify_all(m, log, perturb=False)
+        assert len(ests) == 37
+        for e in (0, 17, 36):
+            one = replay.identify(m, log, e, perturb=False)
+            assert ests[e].n_samples == one.n_samples == log.frame_steps.shape[0]
+            assert np.abs(ests[e].phi - one.phi).max() < 1e-9 * np.abs(one.phi).max()
+        # strided views of the log are consumed in place: the packs equal the oracle's Gram of the logged samples
+        from oracle import rnea_vec as rv
+        e = 5
+        tr = log.trajectory[..., e].cpu().numpy()
+        out = rv.inverse_batched(tr, c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0)
+        Vs, dVs = rv.sensor_frame_twists_batched(c.pose_sen_Rt, out["twists"][:, -1], out["dtwists"][:, -1])
+        ref = rv.gram_pack(rv.regressor_batched(Vs, dVs), log.fts_sen[..., e].cpu().numpy())
+        got = m.regressor_gram_grouped(log.trajectory[:, 0], log.trajectory[:, 1], log.trajectory[:, 2], log.fts_sen)[e].cpu().numpy()
+        assert np.abs(got - ref).max() < 1e-9 * np.abs(ref).max()
+    noisy = replay.identify_all(m, log, perturb=True, seed=3)
+    masses = np.array([x.phi[0] for x in noisy])
+    assert abs(masses.mean() - phi[0]) < 0.05 * phi[0] and masses.std() > 0
