@@ -23,6 +23,9 @@
 namespace rbm {
 
 constexpr int kLinBlock = 128;
+// Occupancy experiments (tools/kbench `lin`, 2^20 states, 200 launches, G states/s): 2 blocks of 128 threads per SM at 254 registers
+// (this setting) 2.76; 3 blocks at 168 registers (~300 B of spills) 2.69; M^-1 parked in shared memory between the column loops
+// 2.75 with 2 blocks, 2.52 with 3.  More resident warps do not pay for the spills: the setting stays at 2.
 #ifndef RBM_LIN_MINB
 #define RBM_LIN_MINB 2
 #endif
