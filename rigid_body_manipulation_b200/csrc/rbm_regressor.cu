@@ -289,7 +289,9 @@ __global__ void __launch_bounds__(kGramBlock, 1) k_regressor_gram(const __grid_c
 //   per-stage `empty` mbarriers + refill one tile late instead of __syncthreads (warps free to drift 3 tiles)   28.8 (fp32 45.6 vs 47.0)
 //   warp-specialised: 8 kinematics warps (setmaxnreg 128) hand [V_s | dV_s | f] through shared memory to
 //     4 accumulator warps (setmaxnreg 240, one per scheduler, 2 samples per tile each)                           25.3 ... 26.9
-// i.e. neither the CTA barrier nor the lock-step phases are the limiter; the FP64 pipe is ~60 % busy and what is left is
+//   fp32 only: accumulators held as float pairs, rank-1 rows as packed FFMA2 with a scalar-broadcast operand
+//     (109 instead of 180 FMA-class instructions per sample, bit-identical sums)                             fp32 44.8 vs 47.0
+// i.e. neither the CTA barrier nor the lock-step phases are the limiter (and FFMA2 buys no issue bandwidth here); the FP64 pipe is ~60 % busy and what is left is
 // dependent-issue latency inside each thread, which only more resident warps (registers!) or less arithmetic would remove.
 // In fp64 the kernel is then bound by the FP64 pipe at 8 warps per SM (250 registers: 70 double accumulators).
 constexpr int kStreams = 24;  // q(6) qd(6) qdd(6) f(6)
