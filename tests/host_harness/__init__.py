@@ -22,7 +22,7 @@ def nvcc_path():
 
 def build():
     os.makedirs(OUT, exist_ok=True)
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rbm_rnea.cuh", "rbm_typed.cuh", "rbm_trig.cuh", "rbm_model.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rbm_rnea.cuh", "rbm_typed.cuh", "rbm_trig.cuh", "rbm_model.cuh", "rbm_dynamics.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     nvcc = nvcc_path()
@@ -89,3 +89,60 @@ def sensor_regressor(pose_Rt, V, dV):
     rc = lib().h_sensor_regressor_f64(_p(np.ascontiguousarray(pose_Rt, dtype=np.float64)), _p(V), _p(dV), _p(Vs), _p(dVs), _p(Y), C.c_int64(n))
     assert rc == 0
     return Vs, dVs, Y
+
+
+def _model_args(analysis):
+    """analysis = engine.analyze_model(...) = (path name, fast params, generic params) -> ctypes-ready (path id, fp, gp, nj)."""
+    path, fast, generic = analysis
+    fp = np.ascontiguousarray(fast, dtype=np.float64)
+    gp = np.ascontiguousarray(generic, dtype=np.float64)
+    return C.c_int(PATH_ID[path]), fp, gp, C.c_int((len(gp) - 42) // 58)
+
+
+def linearize(analysis, q, qd, u=None, dt=0.002, eps=1e-8, centered=True):
+    """q, qd, u: (n, nj) -> A (n, 2nj, 2nj), B (n, 2nj, nj), qdd (n, nj) through csrc/rbm_dynamics.cuh::linearize_state on the host."""
+    path, fp, gp, nj = _model_args(analysis)
+    n, njv = q.shape
+    qs, qds = np.ascontiguousarray(q.T, dtype=np.float64), np.ascontiguousarray(qd.T, dtype=np.float64)
+    us = None if u is None else np.ascontiguousarray(u.T, dtype=np.float64)
+    A, B, qdd = np.zeros((2 * njv, 2 * njv, n)), np.zeros((2 * njv, njv, n)), np.zeros((njv, n))
+    rc = lib().h_linearize_f64(path, _p(fp), _p(gp), nj, _p(qs), _p(qds), _p(us), C.c_double(dt), C.c_double(eps), C.c_int(int(centered)), _p(A), _p(B),
+                               _p(qdd), C.c_int64(n))
+    assert rc == 0
+    return A.transpose(2, 0, 1), B.transpose(2, 0, 1), qdd.T
+
+
+def forward_dynamics(analysis, q, qd, u=None, dt=0.0):
+    path, fp, gp, nj = _model_args(analysis)
+    n, njv = q.shape
+    qs, qds = np.ascontiguousarray(q.T, dtype=np.float64), np.ascontiguousarray(qd.T, dtype=np.float64)
+    us = None if u is None else np.ascontiguousarray(u.T, dtype=np.float64)
+    qdd = np.zeros((njv, n))
+    qn, qdn = (np.zeros((njv, n)), np.zeros((njv, n))) if dt > 0 else (None, None)
+    rc = lib().h_forward_dynamics_f64(path, _p(fp), _p(gp), nj, _p(qs), _p(qds), _p(us), C.c_double(dt), _p(qdd), _p(qn), _p(qdn), C.c_int64(n))
+    assert rc == 0
+    return (qdd.T, qn.T, qdn.T) if dt > 0 else qdd.T
+
+
+def closed_loop(analysis, plan, K, phi, q0, qd0=None, dt=None, fps=50.0, div=None, max_frames=None):
+    """q0 [, qd0]: (n, nj).  Returns dict(frames (F, 3nj+18, n), frame_steps (F,), final (3nj, n)) like engine.Model.closed_loop."""
+    path, fp, gp, nj = _model_args(analysis)
+    n, njv = q0.shape
+    dt = float(plan.timestep if dt is None else dt)
+    div = float(njv if div is None else div)
+    if max_frames is None:
+        max_frames = int(np.ceil(plan.n_steps * dt * fps)) + 2
+    q0s = np.ascontiguousarray(q0.T, dtype=np.float64)
+    qd0s = None if qd0 is None else np.ascontiguousarray(qd0.T, dtype=np.float64)
+    frames = np.zeros((max_frames, 3 * njv + 18, n))
+    fsteps = np.full(max_frames, -1, dtype=np.int32)
+    nfr = np.zeros(1, dtype=np.int32)
+    final = np.zeros((3 * njv, n))
+    Kc, ph = np.ascontiguousarray(K, dtype=np.float64), np.ascontiguousarray(phi, dtype=np.float64)
+    co, di, of = (np.ascontiguousarray(a, dtype=np.float64) for a in (plan.coeffs, plan.displacement, plan.pos_offset))
+    rc = lib().h_closed_loop_f64(path, _p(fp), _p(gp), nj, _p(co), _p(di), _p(of), C.c_double(plan.timestep), C.c_double(plan.init_step),
+                                 C.c_int(plan.n_steps), _p(Kc), _p(ph), C.c_double(dt), C.c_double(fps), C.c_double(div), _p(q0s), _p(qd0s), _p(frames),
+                                 C.c_int(max_frames), _p(fsteps), _p(nfr), _p(final), C.c_int64(n))
+    assert rc == 0
+    nf = min(int(nfr[0]), max_frames)
+    return dict(frames=frames[:nf], frame_steps=fsteps[:nf], final=final)

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY (never part of librbm_b200.so, never reachable from the package).
 //
-// The device arithmetic of the kernels lives in __host__ __device__ headers (csrc/rbm_typed.cuh, rbm_trig.cuh, rbm_rnea.cuh).
+// The device arithmetic of the kernels lives in __host__ __device__ headers (csrc/rbm_typed.cuh, rbm_trig.cuh, rbm_rnea.cuh,
+// rbm_dynamics.cuh).
 // This translation unit instantiates the SAME per-sample functions for the host and exposes them through a tiny C interface,
 // so that the `-m "not gpu"` suite can check the kernels' mathematics -- the structure-specialised typed recursion, the generic
 // recursion, the regressor blocks, the reduced (inertia-only / velocity-only) evaluations -- against the reference-generated
@@ -9,6 +10,7 @@
 #include <cstdint>
 #include <cstring>
 
+#include "rbm_dynamics.cuh"
 #include "rbm_rnea.cuh"
 
 using namespace rbm;
@@ -112,6 +114,58 @@ int h_sensor_regressor_f64(const double* pose_Rt, const double* V, const double*
       }
   }
   return 0;
+}
+
+}  // extern "C"
+
+// ---- rbm_dynamics.cuh: LQR linearisation, forward dynamics / step, closed-loop rollout (same SoA layouts as the kernels) ----------
+namespace {
+template <class F>
+int with_evaluator(int path, const double* fast_params, const double* gp, int nj, F&& body) {
+  if (path == PATH_SEQ_ISO || path == PATH_SEQ_RIGID) {
+    const FastParams<double> P = convert<double>(fast_params);
+    if (path == PATH_SEQ_ISO) { FastEval<double, SeqIso> ev{P}; body(ev); }
+    else { FastEval<double, SeqRigid> ev{P}; body(ev); }
+    return 0;
+  }
+  if (path != PATH_GENERIC || nj < 1 || nj > RBM_MAX_JOINTS) return -1;
+  double zero[18] = {0};
+  GenericEval<double> ev{gp, zero, nj};
+  body(ev);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int h_linearize_f64(int path, const double* fast_params, const double* gp, int nj, const double* q, const double* qd, const double* u, double dt, double eps,
+                    int centered, double* A, double* B, double* qdd, int64_t n) {
+  return with_evaluator(path, fast_params, gp, nj, [&](auto& ev) {
+    for (int64_t s = 0; s < n; ++s) linearize_state<double>(ev, q, qd, u, dt, eps, centered != 0, A, B, qdd, s, n);
+  });
+}
+
+int h_forward_dynamics_f64(int path, const double* fast_params, const double* gp, int nj, const double* q, const double* qd, const double* u, double dt,
+                           double* qdd, double* q_next, double* qd_next, int64_t n) {
+  return with_evaluator(path, fast_params, gp, nj, [&](auto& ev) {
+    for (int64_t s = 0; s < n; ++s) forward_dynamics_state<double>(ev, q, qd, u, dt, qdd, q_next, qd_next, s, n);
+  });
+}
+
+int h_closed_loop_f64(int path, const double* fast_params, const double* gp, int nj, const double* coeffs, const double* disp, const double* offset,
+                      double plan_timestep, double step0, int n_steps, const double* K, const double* phi, double dt, double fps, double div,
+                      const double* q0, const double* qd0, double* frames, int max_frames, int* frame_steps, int* n_frames, double* final_state, int64_t n) {
+  PlanArg<double> pl;
+  for (int k = 0; k < 6; ++k) pl.coeffs[k] = coeffs[k];
+  for (int k = 0; k < RBM_MAX_JOINTS; ++k) { pl.disp[k] = k < nj ? disp[k] : 0.0; pl.offset[k] = k < nj ? offset[k] : 0.0; }
+  pl.inv_dt = 1.0 / plan_timestep;
+  pl.inv_dt2 = 1.0 / (plan_timestep * plan_timestep);
+  pl.step0 = step0;
+  pl.stride = 1.0;
+  return with_evaluator(path, fast_params, gp, nj, [&](auto& ev) {
+    for (int64_t s = 0; s < n; ++s)
+      closed_loop_env<double>(ev, pl, K, phi, dt, fps, div, n_steps, max_frames, q0, qd0, frames, frame_steps, n_frames, final_state, s, n);
+  });
 }
 
 }  // extern "C"
