@@ -83,6 +83,8 @@ def identify(model, log: ReplayLog, env: int = 0, perturb: bool = True, error_ra
     """Post-processing of core/simulate.py:279-290 + loggers.py:127-129 for one environment: optional measurement noise on the
     logged wrenches, then the fused regressor + Gram kernel over the logged (qpos, qvel, qacc) and the 10x10 solve."""
     f = log.fts_sen[..., env].cpu().numpy()
+    if not np.isfinite(f).all():
+        raise ValueError(f"environment {env}: the rollout diverged (non-finite log)")
     if perturb:
         f = idn.perturb_wrench(f, error_rate, seed)
     tr = log.trajectory[..., env]
@@ -106,8 +108,11 @@ def perturb_wrench_device(fts: torch.Tensor, error_rate: float = 0.05, seed: int
 
 
 def identify_all(model, log: ReplayLog, perturb: bool = True, error_rate: float = 0.05, seed: int = 0) -> list:
-    """Identification of EVERY environment of a log: one grouped Gram launch (one environment per thread), then the 10x10 solves."""
+    """Identification of EVERY environment of a log: one grouped Gram launch (one environment per thread), then the 10x10 solves.
+    Returns one identification.Identification per environment, None for environments whose rollout diverged."""
     f = perturb_wrench_device(log.fts_sen, error_rate, seed) if perturb else log.fts_sen
     tr = log.trajectory
-    packs = model.regressor_gram_grouped(tr[:, 0], tr[:, 1], tr[:, 2], f.contiguous() if perturb else f)
-    return idn.solve_many(packs)
+    packs = model.regressor_gram_grouped(tr[:, 0], tr[:, 1], tr[:, 2], f.contiguous() if perturb else f).cpu().numpy()
+    # a rollout can diverge (explicit integration of a fast, heavy wrist; feedback of the reference's sign on a perturbed start): its
+    # log is not finite and it gets no estimate
+    return [idn.solve(p) if np.isfinite(p).all() else None for p in packs]
