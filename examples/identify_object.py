@@ -56,8 +56,8 @@ def main():
     print(f"kernel path {m.kernel_path}; {a.envs} environments x {plan.n_steps} steps in {t_roll * 1e3:.1f} ms, {log.frame_steps.shape[0]} frames each")
     tgt = plan.trajectory()[log.frame_steps.cpu().numpy()]
     err = (log.trajectory[:, 0] - torch.as_tensor(tgt[:, 0], device="cuda")[..., None]).abs().amax(dim=0)      # (nj, envs)
-    finite = torch.isfinite(log.fts_sen).all(dim=0).all(dim=0) & torch.isfinite(err).all(dim=0)
-    print(f"max tracking error per joint over the {int(finite.sum())} environments that stayed finite:",
+    finite = ~log.diverged()
+    print(f"max tracking error per joint over the {int(finite.sum())} environments that did not diverge:",
           np.array2string(err[:, finite].amax(dim=1).cpu().numpy(), precision=4))
     if not bool(finite[0]):
         raise SystemExit("environment 0 diverged: this target / plan is not integrable with the explicit step (try --duration or another target)")

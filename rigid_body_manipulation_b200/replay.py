@@ -59,6 +59,13 @@ class ReplayLog:
             t += self.timestep
         return np.asarray(acc)
 
+    def diverged(self, limit: float = 1e3) -> torch.Tensor:
+        """(n,) bool: environments whose log is not finite or whose joint positions / velocities left +-limit -- an explicit 2 ms Euler
+        step on a fast, heavy wrist (or the reference's feedback sign on a perturbed start) can run away."""
+        tr = self.trajectory[:, :2]
+        bad = ~torch.isfinite(self.fts_sen).all(dim=0).all(dim=0)
+        return bad | ~(tr.abs() < limit).all(dim=0).all(dim=0).all(dim=0)
+
     def env(self, e: int) -> dict:
         """Host copies of one environment, shaped like the reference's post-processed arrays (core/simulate.py:273-277)."""
         return dict(trajectory=self.trajectory[..., e].cpu().numpy(), twists_sen=self.twists_sen[..., e].cpu().numpy(),
@@ -113,6 +120,6 @@ def identify_all(model, log: ReplayLog, perturb: bool = True, error_rate: float 
     f = perturb_wrench_device(log.fts_sen, error_rate, seed) if perturb else log.fts_sen
     tr = log.trajectory
     packs = model.regressor_gram_grouped(tr[:, 0], tr[:, 1], tr[:, 2], f.contiguous() if perturb else f).cpu().numpy()
-    # a rollout can diverge (explicit integration of a fast, heavy wrist; feedback of the reference's sign on a perturbed start): its
-    # log is not finite and it gets no estimate
-    return [idn.solve(p) if np.isfinite(p).all() else None for p in packs]
+    # a rollout can diverge (ReplayLog.diverged): it gets no estimate
+    bad = log.diverged().cpu().numpy()
+    return [None if (bad[e] or not np.isfinite(p).all()) else idn.solve(p) for e, p in enumerate(packs)]

@@ -44,3 +44,19 @@ def test_frame_schedule_and_short_rollout():
     assert abs(np.linalg.norm(out["wrench"][1][:3]) - m_obj * 9.81) < 0.05 * m_obj * 9.81
     # the lagged acceleration: frame k logs qacc of the forward pass one step earlier
     assert np.abs(out["act"][1:, 0] - g["traj"][out["step"][1:], 0]).max() < 1e-3
+
+
+def test_replay_log_flags_diverged_environments():
+    import torch
+
+    from rigid_body_manipulation_b200.replay import ReplayLog
+
+    F, n = 5, 4
+    tr, f = torch.zeros(F, 3, 6, n, dtype=torch.float64), torch.zeros(F, 6, n, dtype=torch.float64)
+    tr[2, 0, 3, 1] = 1e5          # a joint position ran away
+    f[1, 2, 2] = float("nan")     # a non-finite wrench
+    tr[0, 2, 0, 3] = 1e9          # a large logged acceleration alone does not count
+    log = ReplayLog(frame_steps=torch.arange(F, dtype=torch.int32), trajectory=tr, twists_sen=f, dtwists_sen=f, fts_sen=f,
+                    final=torch.zeros(3, 6, n, dtype=torch.float64), timestep=0.002)
+    assert log.diverged().tolist() == [False, True, True, False]
+    assert np.allclose(log.time, [0.0, 0.002, 0.004, 0.006, 0.008])
