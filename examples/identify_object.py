@@ -74,7 +74,8 @@ def main():
         masses = np.array([e.phi[0] for e in good])
         scores = np.array([idn.score(e.phi, phi_true, c.target.aabb_scale) for e in good])
         print(f"\n{len(good)} of {a.envs} environments identified in {t_id * 1e3:.1f} ms ({a.envs - len(good)} rollouts diverged): "
-              f"mass {masses.mean():.5f} +- {masses.std():.5f} kg (truth {phi_true[0]:.5f}), median score {np.median(scores):.3e}")
+              f"mass median {np.median(masses):.5f} kg, quartiles {np.percentile(masses, 25):.5f} .. {np.percentile(masses, 75):.5f} "
+              f"(truth {phi_true[0]:.5f}), median score {np.median(scores):.3e}")
     clean = replay.identify(m, log, 0, perturb=False)
     print(f"\nnoise-free estimate, env 0: score {idn.score(clean.phi, phi_true, c.target.aabb_scale):.3e}, rms residual {clean.rms_residual:.3e} N")
     print("(the reference scores against the object-frame CAD numbers, main.py:79-82; in that frame the score would be "
