@@ -11,15 +11,13 @@
 // result for a given grid).  HBM traffic per sample: q, qd, qdd, f = 24 scalars read, nothing written.
 #include "rbm_async.cuh"
 #include "rbm_internal.h"
+#include "rbm_gram.cuh"
 #include "rbm_rnea.cuh"
 
 namespace rbm {
 
 constexpr int kRowsBlock = 128;
 constexpr int kGramBlock = 256;
-constexpr int kTop = 15;             // 5x5 symmetric: [x | X | f_force]
-constexpr int kBot = 55;             // 10x10 symmetric: [-[x]x | Yb | f_torque]
-constexpr int kAcc = kTop + kBot;    // 70
 
 // ---- last-link twist for one sample, any kernel path ------------------------------------------------
 template <class T, int PATH>
@@ -137,36 +135,7 @@ __global__ void __launch_bounds__(kRowsBlock) k_regressor_from_traj(const __grid
 // ---------------------------------------------------------------------------------------------
 // Gram accumulation
 // ---------------------------------------------------------------------------------------------
-// structural zeros of the bottom block: -[x]x has a zero diagonal (rows 0..2 x cols 0..2)
-__host__ __device__ constexpr bool bot_nz(int r, int c) { return !(c < 3 && c == r); }
-
-// acc layout: [0,15) upper triangle of U^T U (5x5, row-major i<=j), [15,70) upper triangle of W^T W (10x10)
-template <class TA, class T>
-__device__ __forceinline__ void gram_accumulate(TA (&acc)[kAcc], const T (&top)[3][4], const T (&bot)[3][9], const T (&f)[6]) {
-  // U = [top | f_force] (3x5), W = [bot | f_torque] (3x10)
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    TA u[5], w[10];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) u[c] = (TA)top[r][c];
-    u[4] = (TA)f[r];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) w[c] = (TA)bot[r][c];
-    w[9] = (TA)f[3 + r];
-    int k = 0;
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-      for (int j = i; j < 5; ++j) { acc[k] += u[i] * u[j]; ++k; }
-#pragma unroll
-    for (int i = 0; i < 10; ++i)
-#pragma unroll
-      for (int j = i; j < 10; ++j) {
-        if (bot_nz(r, i) && bot_nz(r, j)) acc[k] += w[i] * w[j];
-        ++k;
-      }
-  }
-}
+// bot_nz, gram_accumulate, gram_pack_entry: rbm_gram.cuh (shared with the host harness)
 
 // Per-sample work shared by both Gram kernels: (q, qd, qdd, f) in registers -> regressor blocks -> accumulate.
 template <class T, int PATH>
@@ -394,25 +363,9 @@ __global__ void __launch_bounds__(128) k_gram_finalize(const double* __restrict_
     tot[threadIdx.x] = v;
   }
   __syncthreads();
-  auto tri = [](int n_, int i, int j) { if (i > j) { int t = i; i = j; j = t; } return i * n_ - i * (i - 1) / 2 + (j - i); };
   const int t = threadIdx.x;
-  if (t < 100) {
-    const int a = t / 10, b = t % 10;
-    double v = 0.0;
-    if (a <= 3 && b <= 3) v += tot[tri(5, a, b)];
-    if (a >= 1 && b >= 1) v += tot[kTop + tri(10, a - 1, b - 1)];
-    pack[t] = v;
-  } else if (t < 110) {
-    const int a = t - 100;
-    double v = 0.0;
-    if (a <= 3) v += tot[tri(5, a, 4)];
-    if (a >= 1) v += tot[kTop + tri(10, a - 1, 9)];
-    pack[t] = v;
-  } else if (t == 110) {
-    pack[t] = tot[tri(5, 4, 4)] + tot[kTop + tri(10, 9, 9)];
-  } else if (t == 111) {
-    pack[t] = n_samples;
-  }
+  if (t < 111) pack[t] = gram_pack_entry(tot, t);
+  else if (t == 111) pack[t] = n_samples;
 }
 
 // ---- grouped variant: one Gram pack per GROUP (environment / object), one group per thread ----------------------------------
@@ -447,23 +400,9 @@ __global__ void __launch_bounds__(kRowsBlock) k_regressor_gram_grouped(const __g
     regressor_blocks(Vs, dVs, top, bot);
     gram_accumulate(acc, top, bot, fs);
   }
-  auto tri = [](int n_, int i, int j) { if (i > j) { int t = i; i = j; j = t; } return i * n_ - i * (i - 1) / 2 + (j - i); };
   double* out = packs + g;
 #pragma unroll
-  for (int a = 0; a < 10; ++a) {
-#pragma unroll
-    for (int b = 0; b < 10; ++b) {
-      double v = 0.0;
-      if (a <= 3 && b <= 3) v += acc[tri(5, a, b)];
-      if (a >= 1 && b >= 1) v += acc[kTop + tri(10, a - 1, b - 1)];
-      out[(int64_t)(a * 10 + b) * ld_out] = v;
-    }
-    double v = 0.0;
-    if (a <= 3) v += acc[tri(5, a, 4)];
-    if (a >= 1) v += acc[kTop + tri(10, a - 1, 9)];
-    out[(int64_t)(100 + a) * ld_out] = v;
-  }
-  out[(int64_t)110 * ld_out] = acc[tri(5, 4, 4)] + acc[kTop + tri(10, 9, 9)];
+  for (int t = 0; t < 111; ++t) out[(int64_t)t * ld_out] = gram_pack_entry(acc, t);
   out[(int64_t)111 * ld_out] = (double)n_frames;
 }
 

@@ -22,7 +22,7 @@ def nvcc_path():
 
 def build():
     os.makedirs(OUT, exist_ok=True)
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rbm_rnea.cuh", "rbm_typed.cuh", "rbm_trig.cuh", "rbm_model.cuh", "rbm_dynamics.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rbm_rnea.cuh", "rbm_typed.cuh", "rbm_trig.cuh", "rbm_model.cuh", "rbm_dynamics.cuh", "rbm_gram.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     nvcc = nvcc_path()
@@ -146,3 +146,14 @@ def closed_loop(analysis, plan, K, phi, q0, qd0=None, dt=None, fps=50.0, div=Non
     assert rc == 0
     nf = min(int(nfr[0]), max_frames)
     return dict(frames=frames[:nf], frame_steps=fsteps[:nf], final=final)
+
+
+def regressor_gram(analysis, q, qd, qdd, f):
+    """q, qd, qdd (n, nj), f (n, 6) -> the 112-double pack through gram_accumulate / gram_pack_entry (csrc/rbm_gram.cuh) on the host."""
+    path, fp, gp, nj = _model_args(analysis)
+    n = q.shape[0]
+    arrs = [np.ascontiguousarray(a.T, dtype=np.float64) for a in (q, qd, qdd, f)]
+    pack = np.zeros(112)
+    rc = lib().h_regressor_gram_f64(path, _p(fp), _p(gp), nj, *[_p(a) for a in arrs], _p(pack), C.c_int64(n))
+    assert rc == 0
+    return pack

@@ -9,8 +9,10 @@
 // suite does that through the real C ABI.
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 
 #include "rbm_dynamics.cuh"
+#include "rbm_gram.cuh"
 #include "rbm_rnea.cuh"
 
 using namespace rbm;
@@ -169,3 +171,29 @@ int h_closed_loop_f64(int path, const double* fast_params, const double* gp, int
 }
 
 }  // extern "C"
+
+// ---- rbm_gram.cuh: the fused regressor + Gram accumulation of k_regressor_gram*, one sample after the other ------------------------
+extern "C" int h_regressor_gram_f64(int path, const double* fast_params, const double* gp, int nj, const double* q, const double* qd, const double* qdd,
+                                    const double* f, double* pack, int64_t n) {
+  double acc[kAcc] = {0};
+  int rc = with_evaluator(path, fast_params, gp, nj, [&](auto& ev) {
+    using E = std::decay_t<decltype(ev)>;
+    constexpr int MJ = E::MAXJ;
+    const double* senp = ev.sensor_pose();
+    for (int64_t s = 0; s < n; ++s) {
+      double rq[MJ] = {0}, rqd[MJ] = {0}, rqdd[MJ] = {0}, c[MJ], sn[MJ], V[6], dV[6], Vs[6], dVs[6], fs[6], top[3][4], bot[3][9];
+      for (int k = 0; k < nj; ++k) { rq[k] = q[k * n + s]; rqd[k] = qd[k * n + s]; rqdd[k] = qdd[k * n + s]; }
+      for (int k = 0; k < MJ; ++k) { c[k] = 1.0; sn[k] = 0.0; }
+      for (int k = 0; k < 6; ++k) fs[k] = f[k * n + s];
+      ev.trig(rq, c, sn);
+      ev.last_twists(rq, c, sn, rqd, rqdd, V, dV);
+      sensor_twists(senp, senp + 9, V, dV, Vs, dVs);
+      regressor_blocks(Vs, dVs, top, bot);
+      gram_accumulate(acc, top, bot, fs);
+    }
+  });
+  if (rc != 0) return rc;
+  for (int t = 0; t < 111; ++t) pack[t] = gram_pack_entry(acc, t);
+  pack[111] = (double)n;
+  return 0;
+}

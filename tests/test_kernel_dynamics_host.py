@@ -78,3 +78,24 @@ def test_closed_loop_rollout_matches_the_literal_loop(force_generic):
             want = ref[key].reshape(len(ref["step"]), -1)
             assert np.abs(fr[:, sl] - want).max() < 1e-9 * np.abs(want).max(), (e, key)
         assert np.abs(out["final"][:6, e] - ref["q_final"]).max() < 1e-11 and np.abs(out["final"][6:12, e] - ref["qd_final"]).max() < 1e-11
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_fused_regressor_gram_matches_the_materialised_normal_equations(force_generic):
+    from oracle import rnea_vec as rv
+
+    c = pm.load_packaged("sequential", "uniform_gearbox")
+    an = engine.analyze_model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, pose_sen_llj=c.pose_sen_Rt, force_generic=force_generic)
+    rng = np.random.default_rng(11)
+    n = 300
+    q, qd = _states(rng, n)
+    qdd = rng.standard_normal((n, 6)) * [3, 3, 3, 10, 10, 10]
+    out = rv.inverse_batched(np.stack([q, qd, qdd], axis=1), c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0)
+    Vs, dVs = rv.sensor_frame_twists_batched(c.pose_sen_Rt, out["twists"][:, -1], out["dtwists"][:, -1])
+    Y = rv.regressor_batched(Vs, dVs)
+    phi = ro.inertia_to_phi(ro.sensor_inertia(c.simat_object_llj, c.pose_sen_Rt))
+    f = Y @ phi + 0.01 * rng.standard_normal((n, 6))
+    ref = rv.gram_pack(Y, f)
+    got = host_harness.regressor_gram(an, q, qd, qdd, f)
+    assert got[111] == n
+    assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
