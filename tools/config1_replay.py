@@ -6,7 +6,8 @@ need MuJoCo, timed three ways on this machine:
   dropin_scalar : the same loop through the drop-in `dynamics` package (one tiny GPU launch per call)
   batched       : the whole planned trajectory in one launch per kernel (what the B200 path is for)
 
-Prints one JSON line.  (The closed loop itself -- mj_step feedback -- is out of scope: SURVEY.md 2, row 6.)
+Prints one JSON line.  (The closed loop itself -- state feedback through the plant step -- is `rigid_body_manipulation_b200/replay.py`
+/ `rbm_closed_loop_f64`; see examples/identify_object.py and tools/bench_replay.py.)
 """
 import json
 import os
