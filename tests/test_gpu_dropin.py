@@ -136,3 +136,33 @@ def test_mujoco_bridge_and_state_space(mods):
     consts = dict(hposes_Rt=g["hposes_Rt"], simats=g["simats"], uscrews=g["uscrews"], twist_0=g["twist_0"], dtwist_0=g["dtwist_0"])
     Ar, Br = lo.transition_fd(consts, z["qpos"][None], np.zeros((1, 6)), None, dt=0.002, eps=1e-8)
     assert np.abs(ss.A - Ar[0]).max() < 5e-6 and np.abs(ss.B - Br[0]).max() < 5e-6
+
+
+def test_controller_and_planner_dropins_drive_the_closed_loop(mods):
+    """controllers.LinearQuadraticRegulator (reference controllers/lqr.py:21-51) on the drop-in StateSpace == the gain of the literal
+    restatement; planners.JointPositionPlanner's plan feeds the planner-driven kernels directly."""
+    for k in [k for k in sys.modules if k.split(".")[0] in ("controllers", "planners")]:
+        del sys.modules[k]
+    import controllers
+    import planners
+
+    from oracle import replay_oracle as ro
+    from rigid_body_manipulation_b200 import model as pm
+    from rigid_body_manipulation_b200.engine import Model
+
+    assert os.path.realpath(controllers.__file__).startswith(os.path.realpath(DROPIN))
+    c = pm.load_packaged("sequential", "hammer")
+    state = SimpleNamespace(qpos=c.key_qpos.copy(), qvel=np.zeros(6), ctrl=np.zeros(6))
+    gains = [10.0, 10.0, 10.0, 1e4, 1e4, 1e4]                                   # configurations/base.yaml
+    ctl = controllers.LinearQuadraticRegulator(controllers.LinearQuadraticRegulatorConfig(input_gain=gains), c, state)
+    consts = dict(hposes_Rt=c.hposes_Rt, simats=c.simats, uscrews=c.uscrews, twist_0=c.twist_0, dtwist_0=c.dtwist_0)
+    Kr = ro.lqr_gain(consts, c.key_qpos, np.zeros(6), gains)
+    assert ctl.gain_matrix.shape == (6, 12) and np.abs(ctl.gain_matrix - Kr).max() < 1e-4 * np.abs(Kr).max()
+    dflt = controllers.LinearQuadraticRegulator(controllers.LinearQuadraticRegulatorConfig(), c, state)      # input_gain missing -> ones(nu)
+    assert dflt.input_gain == [1.0] * 6 and dflt.gain_matrix.shape == (6, 12)
+    # planner drop-in -> planner-driven kernel: tau of every planned step without materialising the trajectory
+    pl = planners.JointPositionPlanner(planners.JointPositionPlannerConfig(duration=3.0, displacements=[0.2, 1.4, 0.6, "pi", 0.0, "6 * pi"]), None, state)
+    m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, pose_sen_llj=c.pose_sen_Rt)
+    tau = m.rnea_planned(pl.plan).t().cpu().numpy()
+    g = load_golden("ref_config1_hammer.npz")
+    assert np.abs(tau - g["tau"]).max() < 1e-9 * np.abs(g["tau"]).max()
