@@ -21,7 +21,8 @@ import sys
 
 REFERENCE_ROOT = os.environ.get("RBM_REFERENCE_ROOT", "/root/reference")
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
-_SHADOWED = ("dynamics", "transformations", "planners", "utilities", "liegroups", "mujoco", "omegaconf")
+_SHADOWED = ("dynamics", "transformations", "planners", "utilities", "liegroups", "mujoco", "omegaconf", "matplotlib", "controllers", "sensors",
+             "visualization", "_rbm_ref_simulate")
 
 
 def available() -> bool:
@@ -63,4 +64,43 @@ def load() -> ReferenceModules:
         sys.modules.update(saved_mods)
         sys.path[:] = saved_path
     _cache = ns
+    return ns
+
+
+_sim_cache = None
+
+
+def load_simulation() -> ReferenceModules:
+    """The reference's closed loop, unmodified: `.simulate` (core/simulate.py, loaded by file path because core/__init__.py pulls in
+    dm_control), `.controllers` (controllers/lqr.py), `.planner`, `.dynamics` -- on top of the shims, with `mujoco._functions` bound to
+    the functional stand-in of oracle/mujoco_standin.py and matplotlib stubbed out."""
+    global _sim_cache
+    if _sim_cache is not None:
+        return _sim_cache
+    if not available():
+        raise FileNotFoundError(f"reference checkout not found at {REFERENCE_ROOT}")
+    import importlib.util
+
+    saved_path = list(sys.path)
+    saved_mods = {k: v for k, v in sys.modules.items() if k.split(".")[0] in _SHADOWED}
+    for k in saved_mods:
+        del sys.modules[k]
+    try:
+        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.insert(0, _SHIMS)
+        ns = ReferenceModules()
+        ns.dynamics = importlib.import_module("dynamics")
+        ns.planner = importlib.import_module("planners.joint_position_planner")
+        ns.controllers = importlib.import_module("controllers")
+        spec = importlib.util.spec_from_file_location("_rbm_ref_simulate", os.path.join(REFERENCE_ROOT, "core", "simulate.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ns.simulate = mod
+        assert os.path.realpath(ns.controllers.__file__).startswith(os.path.realpath(REFERENCE_ROOT))
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in _SHADOWED]:
+            del sys.modules[k]
+        sys.modules.update(saved_mods)
+        sys.path[:] = saved_path
+    _sim_cache = ns
     return ns

@@ -124,3 +124,26 @@ def test_grouped_gram_equals_per_environment_grams():
     noisy = replay.identify_all(m, log, perturb=True, seed=3)
     masses = np.array([x.phi[0] for x in noisy])
     assert abs(masses.mean() - phi[0]) < 0.05 * phi[0] and masses.std() > 0
+
+
+def test_kernel_rollout_reproduces_the_reference_simulate_run():
+    """tests/golden/ref_simulate_hammer.npz = what the reference's own simulate() returned (run unmodified on the MuJoCo stand-in,
+    oracle/gen_golden_simulate.py): gain from its LQR class, 150 frames of sensor twists, noisy F/T readings and regressors."""
+    from rigid_body_manipulation_b200.engine import Model, regressor_rows
+
+    g = load_golden("ref_simulate_hammer.npz")
+    m = Model(g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"], pose_sen_llj=g["pose_sen_llj"])
+    pl = planner.QuinticPlan(g["displacements"], g["key_qpos"], float(g["timestep"]), int(g["n_steps"]))
+    K = replay.lqr_gain(m, g["key_qpos"], INPUT_GAIN)
+    assert np.abs(K - g["gain_matrix"]).max() < 1e-4 * np.abs(g["gain_matrix"]).max()     # kernel linearisation + scipy DARE vs the reference's class
+    log = replay.closed_loop_replay(m, pl, g["gain_matrix"], ro.inertia_to_phi(g["G_sensed"]), n_envs=2)
+    got = log.env(1)
+    assert got["twists_sen"].shape == g["twist_sen"].shape
+    assert np.abs(got["twists_sen"] - g["twist_sen"]).max() < 1e-9 * np.abs(g["twist_sen"]).max()
+    assert np.abs(got["dtwists_sen"] - g["dtwist_sen"]).max() < 1e-9 * np.abs(g["dtwist_sen"]).max()
+    assert np.abs(idn.perturb_wrench(got["fts_sen"], 0.05, 0) - g["ft_sen"]).max() < 1e-9 * np.abs(g["ft_sen"]).max()
+    Y = regressor_rows(log.twists_sen[..., 1].contiguous(), log.dtwists_sen[..., 1].contiguous()).cpu().numpy()
+    assert np.abs(Y - g["regressors"]).max() < 1e-9 * np.abs(g["regressors"]).max()
+    est = replay.identify(m, log, 1, perturb=True, seed=0)                                  # same noise stream as the reference's run
+    phi_ref = np.linalg.lstsq(g["regressors"].reshape(-1, 10), g["ft_sen"].reshape(-1), rcond=None)[0]
+    assert np.abs(est.phi - phi_ref).max() < 1e-6 * np.abs(phi_ref).max()
