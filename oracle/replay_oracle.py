@@ -1,8 +1,9 @@
 """ORACLE / TEST INFRASTRUCTURE ONLY -- never imported by the product package.
 
-CPU restatement of the reference's closed-loop main loop, core/simulate.py:185-270, on the MuJoCo stand-in of
-oracle/lqr_oracle.py (MuJoCo 3.3.0 is absent, so this row is PARITY UNPINNED against the reference run itself; what is
-restated from MuJoCo's published behaviour is listed below).  Line by line:
+CPU restatement of the reference's closed-loop main loop, core/simulate.py:185-270, on the plant of oracle/lqr_oracle.py.
+PINNED against the reference's own `simulate()` executed unmodified on the functional MuJoCo stand-in (oracle/mujoco_standin.py;
+tests/test_reference_simulate.py: agreement to 1e-14 on every logged quantity).  MuJoCo 3.3.0 itself is absent, so the pieces of
+MuJoCo's published behaviour that the stand-in and this file share (listed below) remain UNPINNED against MuJoCo.  Line by line:
 
   :186-188  tgt_traj = planner.plan(step); tgt_ctrl = inverse(tgt_traj)[0]
   :191-194  act_traj = (d.qpos, d.qvel, d.qacc)   -- qacc is what the PREVIOUS mj_step's forward pass left in `d`, i.e. it belongs
