@@ -126,12 +126,13 @@ def test_grouped_gram_equals_per_environment_grams():
     assert abs(masses.mean() - phi[0]) < 0.05 * phi[0] and masses.std() > 0
 
 
-def test_kernel_rollout_reproduces_the_reference_simulate_run():
+@pytest.mark.parametrize("target", ["hammer", "uniform_gearbox"])
+def test_kernel_rollout_reproduces_the_reference_simulate_run(target):
     """tests/golden/ref_simulate_hammer.npz = what the reference's own simulate() returned (run unmodified on the MuJoCo stand-in,
     oracle/gen_golden_simulate.py): gain from its LQR class, 150 frames of sensor twists, noisy F/T readings and regressors."""
     from rigid_body_manipulation_b200.engine import Model, regressor_rows
 
-    g = load_golden("ref_simulate_hammer.npz")
+    g = load_golden(f"ref_simulate_{target}.npz")
     m = Model(g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"], pose_sen_llj=g["pose_sen_llj"])
     pl = planner.QuinticPlan(g["displacements"], g["key_qpos"], float(g["timestep"]), int(g["n_steps"]))
     K = replay.lqr_gain(m, g["key_qpos"], INPUT_GAIN)

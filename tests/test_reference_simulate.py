@@ -29,7 +29,7 @@ def _consts(g):
 def test_reference_simulate_equals_the_restated_loop():
     from oracle.gen_golden_simulate import run_reference_simulation
 
-    res, controller, pl, m = run_reference_simulation("uniform_gearbox", duration=0.5)     # 250 steps, 25 frames
+    res, controller, pl, m = run_reference_simulation("kill_la_kill", duration=0.5)        # 250 steps, 25 frames
     K = controller.gain_matrix
     Kr = ro.lqr_gain(m.consts, m.key_qpos, np.zeros(6), [10.0, 10.0, 10.0, 1e4, 1e4, 1e4])
     assert np.abs(K - Kr).max() < 1e-12 * np.abs(Kr).max()            # the reference's controller on the stand-in == the restatement
@@ -43,11 +43,12 @@ def test_reference_simulate_equals_the_restated_loop():
     assert np.abs(np.asarray(res["regressors"]) - out["regressor"]).max() < 1e-12 * np.abs(out["regressor"]).max()
 
 
-def test_rollout_algorithm_reproduces_the_reference_run():
+@pytest.mark.parametrize("target", ["hammer", "uniform_gearbox"])
+def test_rollout_algorithm_reproduces_the_reference_run(target):
     host_harness = pytest.importorskip("host_harness")
     if host_harness.nvcc_path() is None:  # pragma: no cover
         pytest.skip("nvcc is needed to build the host harness")
-    g = load_golden("ref_simulate_hammer.npz")
+    g = load_golden(f"ref_simulate_{target}.npz")
     an = engine.analyze_model(g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"], pose_sen_llj=g["pose_sen_llj"])
     assert an[0] == "seq_iso"
     pl = planner.QuinticPlan(g["displacements"], g["key_qpos"], float(g["timestep"]), int(g["n_steps"]))
