@@ -1,4 +1,7 @@
-"""BASELINE.json configs[0] (the reference's own run: base.yaml, 1500 control steps, two `dynamics.inverse` calls per step,
+"""(Lives under tests/ because it times the CPU oracle next to the GPU path; nothing outside tests/, smoke() and bench.py's CPU arm may
+touch oracle/.)
+
+BASELINE.json configs[0] (the reference's own run: base.yaml, 1500 control steps, two `dynamics.inverse` calls per step,
 a 6x10 regressor at the ~151 frame steps, lstsq at the end, one LQR linearisation) -- the open-loop part that does not
 need MuJoCo, timed three ways on this machine:
 
@@ -18,7 +21,7 @@ from functools import partial
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "rigid_body_manipulation_b200", "dropin"))
 
