@@ -59,9 +59,12 @@ def test_no_silent_cpu_path():
 
 
 def test_product_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "rigid_body_manipulation_b200")
     pat = re.compile(r"^\s*(from|import)\s+oracle\b", re.M)
-    for dirpath, _, files in os.walk(pkg):
+    # the package, and everything else that is not tests / smoke / the bench's CPU arm: tools, examples
+    for top in ("rigid_body_manipulation_b200", "tools", "examples"):
+      for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+        if "_build" in dirpath:
+            continue
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
