@@ -184,21 +184,28 @@ def run_reference_arm(args):
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
 L2_BYTES = 126e6
+BASE_YAML_PLAN = dict(displacement=[0.2, 1.4, 0.6, np.pi, 0.0, 6 * np.pi], pos_offset=[1, 1, 1, 0, 0, 0], timestep=0.002, n_steps=1500)
 
 
 class RneaWorkload:
     """configs[1] (and, with --dtype f32 / --samples, the configs[4] sweep): tau for B resident samples."""
     metric, unit = METRIC, UNIT
     launches_per_step = 1
+    name = "rnea"
 
-    def __init__(self, args, model, rank, torch):
-        self.torch, self.model, self.B = torch, model, args.samples
-        self.esize = 8 if args.dtype == "f64" else 4
-        self.tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    def __init__(self, args, model, rank, torch, dtype=None, samples=None, host_buffers=True):
+        dtype = dtype or args.dtype
+        self.torch, self.model, self.B = torch, model, samples or args.samples
+        self.dtype = dtype
+        self.esize = 8 if dtype == "f64" else 4
+        self.tdt = torch.float64 if dtype == "f64" else torch.float32
         self.alg_bytes = 24 * self.esize * self.B  # SURVEY.md 8(d): 18 scalars read + 6 written per sample
-        self.workload = WORKLOAD if (self.B == 1 << 20 and args.dtype == "f64") else f"batched inverse dynamics, {self.B} synthetic samples, {args.dtype}, base.yaml manipulator + hammer"
-        host = sample_states(np.random.default_rng(1000 + rank), self.B).astype(np.float64 if args.dtype == "f64" else np.float32)
-        self.traj_pinned = torch.as_tensor(host).pin_memory()
+        live = int(model.live_inputs().sum())
+        self.moved_bytes = (live + 6) * self.esize * self.B  # rows the kernel really loads + the 6 rows of tau it stores
+        self.live_rows = live
+        self.workload = WORKLOAD if (self.B == 1 << 20 and dtype == "f64") else f"batched inverse dynamics, {self.B} synthetic samples, {dtype}, base.yaml manipulator + hammer"
+        npdt = np.float64 if dtype == "f64" else np.float32
+        host = sample_states(np.random.default_rng(1000 + rank), self.B).astype(npdt)
         # L2 rule: rotate over enough independent buffer sets that the data touched between two uses of one set
         # exceeds 3x the 126 MB L2, so no timed launch can be served from cache
         self.nset = 1 if self.alg_bytes > 16 * L2_BYTES else max(2, int(np.ceil(3 * L2_BYTES / self.alg_bytes)) + 1)
@@ -211,10 +218,19 @@ class RneaWorkload:
             self.sets.append((q, qd, qdd, torch.empty_like(q)))
         del dev
         self.k = 0
-        self.tau_host = torch.empty((self.B, 6), dtype=self.tdt).pin_memory()
         self.layout = "SoA [3][6][B] resident in HBM"
-        self.h2d, self.d2h = 18 * self.esize * self.B, 6 * self.esize * self.B
-        self.e2e_api = "Model.rnea_host -> rbm_rnea_host_* (pinned host AoS traj in, pinned host tau out, chunked 3-stream pipeline)"
+        if host_buffers:  # pinned host buffers of the end-to-end legs (allocated AFTER the NUMA binding of the process)
+            self.traj_pinned = torch.as_tensor(host).pin_memory()                       # AoS (B, 3, 6): the reference's traj layout
+            self.soa_pinned = [torch.as_tensor(np.ascontiguousarray(host[:, k, :].T)).pin_memory() for k in range(3)]  # (6, B) each
+            self.tau_host = torch.empty((self.B, 6), dtype=self.tdt).pin_memory()
+            self.tau_host_soa = torch.empty((6, self.B), dtype=self.tdt).pin_memory()
+            from rigid_body_manipulation_b200 import planner
+
+            self.plan = planner.QuinticPlan(**BASE_YAML_PLAN)
+        # headline e2e: SoA host buffers, live rows only
+        self.h2d, self.d2h = live * self.esize * self.B, 6 * self.esize * self.B
+        self.e2e_api = (f"Model.rnea_host_soa -> rbm_rnea_host_soa_* (pinned host SoA q,qd,qdd in, pinned host tau out; the {live} rows the kernel reads are uploaded "
+                        "(rbm_model_live_inputs), strided cudaMemcpy2DAsync per chunk, 3-stream pipeline)")
 
     def step(self):
         q, qd, qdd, tau = self.sets[self.k % self.nset]
@@ -222,25 +238,42 @@ class RneaWorkload:
         self.model.rnea(q, qd, qdd, tau=tau)
 
     def e2e_step(self):
-        self.model.rnea_host(self.traj_pinned, tau=self.tau_host)
+        self.model.rnea_host_soa(*self.soa_pinned, tau=self.tau_host_soa)
+
+    # other end-to-end shapes of the same metric, reported beside the headline one
+    def e2e_variants(self):
+        B, es = self.B, self.esize
+        stride = self.plan.n_steps / B  # B samples spread over the planned 1500 steps (fractional steps of the same quintic)
+        return {
+            "aos_host": (lambda: self.model.rnea_host(self.traj_pinned, tau=self.tau_host), 18 * es * B, 6 * es * B,
+                         "Model.rnea_host -> rbm_rnea_host_*: the reference's (B,3,6) traj layout, all 18 values per sample uploaded"),
+            "planned_host": (lambda: self.model.rnea_planned_host(self.plan, n=B, step0=0.0, stride=stride, dtype=self.tdt, tau=self.tau_host_soa), 0, 6 * es * B,
+                             "Model.rnea_planned_host -> rbm_rnea_planned_host_*: base.yaml quintic evaluated in the kernel, only tau crosses the bus"),
+        }
 
 
 class GramWorkload:
     """configs[2] per-rank share: fused sensor-frame regressor + Gram of B samples (+ one 112-double all-reduce when N > 1)."""
     metric, unit = "regressor_gram_samples_per_s", "samples/s"
     launches_per_step = 2  # accumulate + finalize
+    name = "gram"
 
-    def __init__(self, args, model, rank, torch):
+    def __init__(self, args, model, rank, torch, dtype=None, samples=None, host_buffers=True):
         from rigid_body_manipulation_b200 import distributed
 
-        self.torch, self.model, self.B, self.dist = torch, model, args.samples, distributed
-        self.esize = 8 if args.dtype == "f64" else 4
-        self.tdt = torch.float64 if args.dtype == "f64" else torch.float32
+        dtype = dtype or args.dtype
+        self.torch, self.model, self.B, self.dist = torch, model, samples or args.samples, distributed
+        self.dtype = dtype
+        self.esize = 8 if dtype == "f64" else 4
+        self.tdt = torch.float64 if dtype == "f64" else torch.float32
         self.alg_bytes = 24 * self.esize * self.B  # q, qd, qdd, f read; nothing written per sample
-        self.workload = f"configs[2] per-GPU share: regressor + Y^T Y / Y^T f Gram over {self.B} synthetic samples, {args.dtype}"
+        live = int(model.live_inputs().sum())
+        self.moved_bytes = (live + 6) * self.esize * self.B  # live rows of q, qd, qdd + the 6 rows of f
+        self.live_rows = live
+        self.workload = f"configs[2] per-GPU share: regressor + Y^T Y / Y^T f Gram over {self.B} synthetic samples, {dtype}"
         gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
         B = self.B
-        self.nset = max(2, int(np.ceil(3 * L2_BYTES / self.alg_bytes)) + 1)
+        self.nset = 1 if self.alg_bytes > 16 * L2_BYTES else max(2, int(np.ceil(3 * L2_BYTES / self.alg_bytes)) + 1)
         phi = np.array([0.585, -0.0032, 1.9e-5, -8e-6, 3.85e-3, 2.9e-3, 3.0e-3, 1e-5, 2e-5, -1e-5])
         self.sets = []
         for _ in range(self.nset):
@@ -255,9 +288,11 @@ class GramWorkload:
             self.sets.append((q, qd, qdd, f))
         self.pack = torch.empty(112, dtype=torch.float64, device="cuda")
         self.k = 0
+        self.reducer = distributed.allreduce_gram  # torch.distributed / NCCL; replaced by NcclGramReducer for the second collective
         self.layout = "SoA q,qd,qdd,f [6][B] resident in HBM"
-        self.host = [t.cpu().pin_memory() for t in self.sets[0]]
-        self.stage = [torch.empty_like(t) for t in self.sets[0]]
+        if host_buffers:
+            self.host = [t.cpu().pin_memory() for t in self.sets[0]]
+            self.stage = [torch.empty_like(t) for t in self.sets[0]]
         self.h2d, self.d2h = 24 * self.esize * B, 112 * 8
         self.e2e_api = "pinned host q,qd,qdd,f -> cudaMemcpyAsync -> Model.regressor_gram -> pack.cpu()"
 
@@ -265,36 +300,64 @@ class GramWorkload:
         q, qd, qdd, f = self.sets[self.k % self.nset]
         self.k += 1
         self.model.regressor_gram(q, qd, qdd, f, pack=self.pack)
-        self.dist.allreduce_gram(self.pack)
+        self.reducer(self.pack)
+
+    def local_step(self):
+        """the same without the collective"""
+        q, qd, qdd, f = self.sets[self.k % self.nset]
+        self.k += 1
+        self.model.regressor_gram(q, qd, qdd, f, pack=self.pack)
 
     def e2e_step(self):
         for h, d in zip(self.host, self.stage):
             d.copy_(h, non_blocking=True)
         self.model.regressor_gram(*self.stage, pack=self.pack)
-        self.dist.allreduce_gram(self.pack)
+        self.reducer(self.pack)
         return self.pack.cpu()
+
+    def e2e_variants(self):
+        return {}
+
+
+def planned_states(rng, n, sigma=0.05):
+    """configs[3] / SURVEY.md 8(d) config 4: joint states along the planned base.yaml trajectory -- a random (fractional) step of
+    the quintic per state -- plus a small N(0, sigma) offset on positions and velocities."""
+    from rigid_body_manipulation_b200 import planner
+
+    plan = planner.QuinticPlan(**BASE_YAML_PLAN)
+    traj = plan.trajectory(rng.uniform(0.0, plan.n_steps, n))  # (n, 3, 6)
+    q = traj[:, 0, :] + sigma * rng.standard_normal((n, 6))
+    qd = traj[:, 1, :] + sigma * rng.standard_normal((n, 6))
+    return q, qd
 
 
 class LinearizeWorkload:
     """configs[3]: A (12x12), B (12x6) of the discrete transition at B joint states (RNEA-based finite differences)."""
     metric, unit = "lqr_linearizations_per_s", "states/s"
     launches_per_step = 1
+    name = "linearize"
 
-    def __init__(self, args, model, rank, torch):
-        self.torch, self.model, self.B = torch, model, args.samples
+    def __init__(self, args, model, rank, torch, dtype=None, samples=None, host_buffers=True):
+        self.torch, self.model, self.B = torch, model, samples or args.samples
+        self.dtype = "f64"
         self.esize, self.tdt = 8, torch.float64
         self.alg_bytes = 228 * 8 * self.B  # 12 scalars read, 144 + 72 written per state (SURVEY.md 8(d))
-        self.workload = f"configs[3]: LQR linearisation (A 12x12, B 12x6) at {self.B} joint states, centred FD eps 1e-8, dt 0.002, f64"
-        host = sample_states(np.random.default_rng(2000 + rank), self.B)
-        dev = torch.as_tensor(host, device="cuda")
-        self.q, self.qd = dev[:, 0, :].t().contiguous(), dev[:, 1, :].t().contiguous()
-        self.qh, self.qdh = self.q.cpu().pin_memory(), self.qd.cpu().pin_memory()
+        live_q = int(model.live_inputs()[0].sum())
+        self.moved_bytes = (live_q + 6 + 216) * 8 * self.B
+        self.live_rows = live_q + 6
+        self.workload = (f"configs[3]: LQR linearisation (A 12x12, B 12x6) at {self.B} joint states along the planned base.yaml trajectory "
+                         "(random step + N(0, 0.05)), centred FD eps 1e-8, dt 0.002, f64")
+        q, qd = planned_states(np.random.default_rng(2000 + rank), self.B)
+        self.q = torch.as_tensor(np.ascontiguousarray(q.T), device="cuda")
+        self.qd = torch.as_tensor(np.ascontiguousarray(qd.T), device="cuda")
         self.nset = 1
         self.layout = "SoA q,qd [6][B] in; element-major A [144][B], B [72][B] out (output alone is 1.7 KB/state >> L2 for B = 2^20)"
         self.h2d, self.d2h = 12 * 8 * self.B, 216 * 8 * self.B
         self.e2e_api = "pinned host q,qd -> Model.linearize -> A,B copied to pinned host"
-        self.Ah = torch.empty((12, 12, self.B), dtype=self.tdt).pin_memory()
-        self.Bh = torch.empty((12, 6, self.B), dtype=self.tdt).pin_memory()
+        if host_buffers:
+            self.qh, self.qdh = self.q.cpu().pin_memory(), self.qd.cpu().pin_memory()
+            self.Ah = torch.empty((12, 12, self.B), dtype=self.tdt).pin_memory()
+            self.Bh = torch.empty((12, 6, self.B), dtype=self.tdt).pin_memory()
 
     def step(self):
         self.out = self.model.linearize(self.q, self.qd, None, dt=0.002, eps=1e-8, centered=True)
@@ -306,8 +369,173 @@ class LinearizeWorkload:
         self.Bh.copy_(Bm.permute(1, 2, 0), non_blocking=True)
         self.torch.cuda.synchronize()
 
+    def e2e_variants(self):
+        return {}
+
 
 WORKLOADS = {"rnea": RneaWorkload, "gram": GramWorkload, "linearize": LinearizeWorkload}
+
+
+class Timer:
+    """Device-side timing shared by the primary workload and the extras: barrier + synchronize on both sides, CUDA events on the
+    launching stream, max over ranks.  Every count that governs a loop containing a collective is identical on all ranks."""
+
+    def __init__(self, torch, dist, world):
+        self.torch, self.dist, self.world = torch, dist, world
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def heat_count(self, step, seconds):
+        """how many untimed steps fill `seconds` -- derived from a max-reduced estimate, never from a per-rank wall-clock loop"""
+        t0 = time.perf_counter()
+        for _ in range(3):
+            step()
+        self.torch.cuda.synchronize()
+        (est,) = self.max_over_ranks([(time.perf_counter() - t0) / 3])
+        return int(min(20000, max(10, seconds / max(est, 1e-6))))
+
+    def timed(self, step, steps):
+        """total ms for exactly `steps` back-to-back steps (max over ranks)"""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks([e0.elapsed_time(e1)])[0]
+
+    def isolated(self, step, steps):
+        """mean of per-launch event pairs (contains the stream bubbles the event records insert)"""
+        torch = self.torch
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            a.record()
+            step()
+            b.record()
+        self.barrier()
+        return self.max_over_ranks([float(np.mean([a.elapsed_time(b) for a, b in evs]))])[0]
+
+    def wall(self, step, steps, warm):
+        """host wall-clock seconds for `steps` calls of a synchronous end-to-end step (max over ranks)"""
+        for _ in range(warm):
+            step()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        self.barrier()
+        return self.max_over_ranks([time.perf_counter() - t0])[0]
+
+
+def roofline_block(wl, kern_ms_avg, kern_ms_isolated, traffic):
+    peak, peak_src = measured_peak_gbs()
+    achieved = wl.alg_bytes / (kern_ms_avg * 1e-3) / 1e9
+    moved = wl.moved_bytes / (kern_ms_avg * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": peak_src, "kernel_ms": kern_ms_avg, "kernel_ms_isolated": kern_ms_isolated,
+            "algorithmic_bytes_per_launch": wl.alg_bytes,
+            # the kernel does not load rows its result cannot depend on (rbm_model_live_inputs): `frac` is on SURVEY 8(d)'s contract
+            # bytes, `frac_moved` on the bytes the launch really moves through DRAM
+            "bytes_moved_per_launch": wl.moved_bytes, "achieved_moved": moved, "frac_moved": moved / peak, "live_input_rows": wl.live_rows}
+
+
+def traffic_entry(key):
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            return json.load(f).get(key)
+    return None
+
+
+def gram_extra(args, model, rank, world, local, torch, dist, tm, dtype):
+    """configs[2] share of this rank (12.5 M samples; 100 M at 8 GPUs) with the all-reduce INSIDE the timed step, through both
+    collectives, plus the collective timed alone and parity of the reduced pack."""
+    from rigid_body_manipulation_b200 import distributed
+
+    wl = GramWorkload(args, model, rank, torch, dtype=dtype, samples=args.gram_samples, host_buffers=False)
+    steps = max(5, min(args.steps, 20))
+    out = {"samples_per_gpu": wl.B, "samples_total": wl.B * world, "dtype": dtype, "steps": steps}
+    for _ in range(3):
+        wl.step()
+    n_heat = tm.heat_count(wl.step, 0.15)
+    for _ in range(n_heat):
+        wl.step()
+    ms = tm.timed(wl.step, steps)
+    out["collective"] = "torch-nccl" if world > 1 else "none (1 rank)"
+    out["value"] = world * wl.B * steps / (ms * 1e-3)
+    out["ms_per_step"] = ms / steps
+    rl = roofline_block(wl, ms / steps, None, traffic_entry(f"gram_{dtype}_{wl.B}"))
+    out.update(frac=rl["frac"], frac_moved=rl["frac_moved"], achieved=rl["achieved"], achieved_moved=rl["achieved_moved"])
+    ms_local = tm.timed(wl.local_step, steps)
+    out["ms_per_step_no_collective"] = ms_local / steps
+    # parity of the reduced pack: local packs gathered and summed on the host in rank order vs the all-reduced pack
+    wl.k = 0
+    wl.local_step()
+    local_pack = wl.pack.clone()
+    torch.cuda.synchronize()
+    if world > 1:
+        gathered = [torch.empty_like(local_pack) for _ in range(world)]
+        dist.all_gather(gathered, local_pack)
+        ref = torch.stack(gathered).cpu().numpy().sum(axis=0)
+        p1 = local_pack.clone()
+        distributed.allreduce_gram(p1)
+        red = distributed.NcclGramReducer(local)  # the C ABI's own collective (rbm_allreduce_gram_n); constructed collectively
+        p2 = local_pack.clone()
+        red(p2)
+        torch.cuda.synchronize()
+        a1, a2 = p1.cpu().numpy(), p2.cpu().numpy()
+        scale = np.abs(ref[:100]).max()
+        out["pack_n_ok"] = bool(a1[111] == world * wl.B and a2[111] == world * wl.B)
+        out["pack_matches_allgather_sum"] = bool(np.abs(a1 - ref).max() <= 1e-12 * scale)
+        out["pack_vs_allgather_max_rel"] = float(np.abs(a1 - ref).max() / scale)
+        out["collectives_bit_identical"] = bool(np.array_equal(a1, a2))
+        # the collective alone (both bindings), and the whole step again through the library's own collective
+        scratch = local_pack.clone()
+        n_ar = 200
+        ms_ar = tm.timed(lambda: distributed.allreduce_gram(scratch), n_ar)
+        scratch.copy_(local_pack)
+        ms_ar2 = tm.timed(lambda: red(scratch), n_ar)
+        out["allreduce_us"] = 1e3 * ms_ar / n_ar
+        out["allreduce_us_rbm"] = 1e3 * ms_ar2 / n_ar
+        wl.reducer = red
+        for _ in range(3):
+            wl.step()
+        ms2 = tm.timed(wl.step, steps)
+        out["rbm_allreduce_gram_n"] = {"value": world * wl.B * steps / (ms2 * 1e-3), "ms_per_step": ms2 / steps,
+                                       "frac": wl.alg_bytes / (ms2 / steps * 1e-3) / 1e9 / rl["peak"]}
+        red.close()
+    else:
+        out["pack_n_ok"] = bool(local_pack[111].item() == wl.B)
+    del wl
+    torch.cuda.empty_cache()
+    return out
+
+
+def small_extra(cls, args, model, rank, world, torch, tm, dtype, samples):
+    wl = cls(args, model, rank, torch, dtype=dtype, samples=samples, host_buffers=False)
+    steps = max(5, min(args.steps, 20))
+    for _ in range(3):
+        wl.step()
+    for _ in range(tm.heat_count(wl.step, 0.1)):
+        wl.step()
+    ms = tm.timed(wl.step, steps)
+    rl = roofline_block(wl, ms / steps, None, traffic_entry(f"{wl.name}_{wl.dtype}_{wl.B}"))
+    out = {"workload": wl.workload, "metric": wl.metric, "unit": wl.unit, "value": world * wl.B * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
+           "frac": rl["frac"], "frac_moved": rl["frac_moved"], "achieved": rl["achieved"], "achieved_moved": rl["achieved_moved"], "traffic": rl["traffic"]}
+    del wl
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_gpu_arm(args):
@@ -320,6 +548,15 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # NUMA: pin this rank (and therefore the pinned host buffers it allocates below) to the GPU's own socket
+    numa = {"bound": False, "why": "disabled (--no-numa)"}
+    if not args.no_numa:
+        from rigid_body_manipulation_b200 import numa as rbm_numa
+
+        try:
+            numa = rbm_numa.bind_to_device(local)
+        except Exception as e:  # pragma: no cover - depends on the box
+            numa = {"bound": False, "why": f"{type(e).__name__}: {e}"}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -329,52 +566,21 @@ def run_gpu_arm(args):
     model = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, pose_sen_llj=c.pose_sen_Rt, device=local)
     wl = WORKLOADS[args.workload](args, model, rank, torch)
     B = wl.B
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    tm = Timer(torch, dist, world)
 
     # ---- device-resident throughput -------------------------------------------------------------------
     for _ in range(args.warmup):
         wl.step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # how many untimed steps fill ~0.3 s (so that the clock sampler sees loaded clocks).  The count must be IDENTICAL on every
-    # rank -- a step may contain a collective (Gram all-reduce) -- so it is derived from a max-reduced estimate, never from a
-    # per-rank wall-clock loop.
-    t0 = time.perf_counter()
-    for _ in range(3):
-        wl.step()
-    torch.cuda.synchronize()
-    est = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(est, op=dist.ReduceOp.MAX)
-    n_heat = int(min(20000, max(10, 0.3 / max(est.item(), 1e-6))))
-    barrier()
+    tm.barrier()
+    n_heat = tm.heat_count(wl.step, 0.3)  # ~0.3 s of untimed steps so that the clock sampler sees loaded clocks
+    tm.barrier()
     with ClockSampler(local) as clk:
         for _ in range(n_heat):
             wl.step()
         # pass 1 -- the reported value: exactly K steps back to back, bracketed by barrier + synchronize
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            wl.step()
-        e1.record()
-        barrier()
-        total_ms = e0.elapsed_time(e1)
-        # pass 2 -- per-launch durations for the roofline (an event pair around every launch, same stream)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for a, b in evs:
-            a.record()
-            wl.step()
-            b.record()
-        barrier()
-    kern_ms = [a.elapsed_time(b) for a, b in evs]
-    t = torch.tensor([total_ms, float(np.mean(kern_ms))], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms_isolated = t.tolist()
+        total_ms = tm.timed(wl.step, args.steps)
+        # pass 2 -- per-launch durations (an event pair around every launch, same stream)
+        kern_ms_isolated = tm.isolated(wl.step, args.steps)
     # one step == one launch of the dominant kernel (plus, for the Gram workload, a single-CTA finalisation): its average
     # launch duration over the timed region is total / K.  The isolated figure (event pair around every launch) additionally
     # contains the stream bubbles that event records insert between launches and is reported for reference.
@@ -382,43 +588,55 @@ def run_gpu_arm(args):
     value = world * B * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the public API (pinned host buffers; H2D + kernel + D2H inside the timed region) ----
-    for _ in range(max(1, min(args.warmup, 3))):
-        wl.e2e_step()
     e2e_steps = max(1, min(args.steps, 20))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        wl.e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    e2e_warm = max(1, min(args.warmup, 3))
+    e2e_s = tm.wall(wl.e2e_step, e2e_steps, e2e_warm)
+    e2e_value = world * B * e2e_steps / e2e_s
+    e2e_variants = {}
+    for name, (fn, h2d, d2h, api) in wl.e2e_variants().items():
+        s_ = tm.wall(fn, e2e_steps, e2e_warm)
+        e2e_variants[name] = {"value": world * B * e2e_steps / s_, "unit": wl.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api}
+    numa_all = [None] * world
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / t.item()
+        dist.all_gather_object(numa_all, {k: numa.get(k) for k in ("pci", "numa_node", "bound", "n_cpus", "mempolicy", "why")})
+    else:
+        numa_all = [{k: numa.get(k) for k in ("pci", "numa_node", "bound", "n_cpus", "mempolicy", "why")}]
+
+    # ---- the other BASELINE configs, attached to the same line (every rank takes part: some contain collectives) ----
+    extra = {}
+    if args.workload == "rnea" and not args.no_extra:
+        del wl.sets
+        torch.cuda.empty_cache()
+        extra["gram"] = {"f64": gram_extra(args, model, rank, world, local, torch, dist, tm, "f64"),
+                         "f32": gram_extra(args, model, rank, world, local, torch, dist, tm, "f32")}
+        extra["linearize"] = small_extra(LinearizeWorkload, args, model, rank, world, torch, tm, "f64", 1 << 20)
+        extra["rnea_f32"] = small_extra(RneaWorkload, args, model, rank, world, torch, tm, "f32", 1 << 24)
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        achieved = wl.alg_bytes / (kern_ms_avg * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get(f"{args.workload}_{args.dtype}_{B}")
         line = {
             "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.dtype if args.workload != "linearize" else "f64", "data": "synthetic",
+            "dtype": wl.dtype, "data": "synthetic",
             "config": {"workload": wl.workload, "batch_per_gpu": B, "layout": wl.layout, "kernel_path": model.kernel_path,
-                       "l2_policy": f"{wl.nset} rotating buffer set(s) x {wl.alg_bytes / 1e6:.0f} MB algorithmic bytes per step (L2 = 126 MB)",
-                       "parallelism": f"samples sharded x{world}" + (", one 112-double NCCL all-reduce per step" if args.workload == "gram" and world > 1 else ", no collective")},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel_ms": kern_ms_avg, "kernel_ms_isolated": kern_ms_isolated,
-                         "algorithmic_bytes_per_launch": wl.alg_bytes},
-            "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h, "api": wl.e2e_api, "steps": e2e_steps},
+                       "l2_policy": (f"{wl.nset} rotating buffer set(s) x {wl.alg_bytes / 1e6:.0f} MB algorithmic bytes per step (L2 = 126 MB)" if wl.nset > 1
+                                     else f"inputs of one step ({wl.alg_bytes / 1e6:.0f} MB) exceed the 126 MB L2"),
+                       "parallelism": (f"samples sharded x{world}, no collective on this workload" if args.workload != "gram" or world == 1
+                                       else f"samples sharded x{world}, one 112-double NCCL all-reduce per step")
+                       + ("; extra.gram: configs[2] share per rank with the NCCL all-reduce inside the timed step" if extra else ""),
+                       "numa": numa_all},
+            "roofline": roofline_block(wl, kern_ms_avg, kern_ms_isolated, traffic_entry(f"{args.workload}_{wl.dtype}_{B}")),
+            "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h, "api": wl.e2e_api, "steps": e2e_steps,
+                    "variants": e2e_variants},
             "gpu_launches": args.steps * wl.launches_per_step,
             "clocks": clk.summary(),
         }
+        if extra:
+            line["extra"] = extra
         if world == 1 and not args.no_cpu and args.workload == "rnea":
+            if numa.get("bound"):  # the CPU leg forks one worker per host core: undo the socket-local CPU binding first
+                from rigid_body_manipulation_b200 import numa as rbm_numa
+
+                rbm_numa.restore_affinity(numa)
             consts = consts_dict(c)
             cores = os.cpu_count() or 1
             rate, _, _ = cpu_reference_rate(consts, cores * 100, cores)  # calibration
@@ -428,6 +646,7 @@ def run_gpu_arm(args):
                                     "sample": f"{n_cpu} samples of the same distribution, per-sample oracle port of reference dynamics.inverse, {wall:.1f} s wall on {cores} processes"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -442,6 +661,9 @@ def main():
     ap.add_argument("--samples", type=int, default=1 << 20, help="samples (states) per GPU per step")
     ap.add_argument("--cpu-samples", type=int, default=0, help="CPU baseline sample count (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra.* legs (configs[2] Gram + all-reduce, configs[3] linearisation, fp32 RNEA)")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the GPU's NUMA node")
+    ap.add_argument("--gram-samples", type=int, default=12_500_000, help="samples per GPU of the extra.gram leg (12.5 M x 8 GPUs = configs[2]'s 100 M)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -61,6 +61,9 @@ enum {
 RBM_API const char* rbm_version(void);
 RBM_API const char* rbm_last_error_string(void); /* thread-local */
 RBM_API int rbm_device_count(void);              /* 0 when no CUDA device / driver is present */
+/* PCI bus id ("0000:1b:00.0"-style, lower-cased by the caller for sysfs) of a CUDA device, as the runtime numbers it (i.e. after
+ * CUDA_VISIBLE_DEVICES).  Host plumbing for NUMA placement of the pinned buffers the *_host entry points stream from. */
+RBM_API int rbm_device_pci_bus_id(int device, char* out, int len);
 
 /* ---- model ------------------------------------------------------------------------------------------
  * Binds the arguments that reference core/simulate.py:150-156 binds with functools.partial onto
@@ -131,6 +134,29 @@ RBM_API int rbm_rnea_planned_f32(const rbm_model* m, const double* coeffs, const
  * complete.  chunk <= 0 picks a default. */
 RBM_API int rbm_rnea_host_f64(const rbm_model* m, const double* traj_host, double* tau_host, int64_t n, int64_t chunk);
 RBM_API int rbm_rnea_host_f32(const rbm_model* m, const float* traj_host, float* tau_host, int64_t n, int64_t chunk);
+
+/* Which rows of (q, qd, qdd) the model's inverse-dynamics kernels read: mask [3][nj], 1 = live, 0 = the result does not depend on
+ * it and the kernel never loads it.  For the reference's structure (three leading prismatic joints, core/simulate.py:98-110,
+ * xml_models/manipulators/sequential.xml:13-39) tau, V_6 and dV_6 do not depend on the gantry positions q_0..q_2, so 15 of the
+ * 18 input rows are live: 168 instead of 192 bytes of DRAM traffic per fp64 sample, and 15 rows instead of 18 over PCIe. */
+RBM_API int rbm_model_live_inputs(const rbm_model* m, int32_t* mask);
+
+/* The same end-to-end path for the kernels' own SoA layout (what dynamics.inverse would be handed by a caller that batches a
+ * whole trajectory: rows of q, qd, qdd): q_host, qd_host, qdd_host, tau_host are HOST buffers [nj][ld].  Only LIVE rows
+ * (rbm_model_live_inputs) are uploaded -- one strided cudaMemcpy2DAsync per run of live rows and chunk -- and tau comes back
+ * with one strided copy per chunk, both overlapped with the kernel over three internal streams.  Synchronous. */
+RBM_API int rbm_rnea_host_soa_f64(const rbm_model* m, const double* q_host, const double* qd_host, const double* qdd_host, double* tau_host,
+                          int64_t n, int64_t ld, int64_t chunk);
+RBM_API int rbm_rnea_host_soa_f32(const rbm_model* m, const float* q_host, const float* qd_host, const float* qdd_host, float* tau_host, int64_t n,
+                          int64_t ld, int64_t chunk);
+
+/* Planner-driven end to end (planners/joint_position_planner.py:86-131 feeding dynamics.inverse, core/simulate.py:187-188): the
+ * trajectory is generated inside the kernel as in rbm_rnea_planned_*, so nothing is uploaded; tau_host [nj][ld] is a HOST buffer
+ * filled chunk by chunk while the next chunk computes.  Synchronous. */
+RBM_API int rbm_rnea_planned_host_f64(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double timestep,
+                              double step0, double stride, double* tau_host, int64_t n, int64_t ld, int64_t chunk);
+RBM_API int rbm_rnea_planned_host_f32(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double timestep,
+                              double step0, double stride, float* tau_host, int64_t n, int64_t ld, int64_t chunk);
 
 /* ---- sensor-frame regressor and identification ------------------------------------------------------
  * Parameter order phi = [m, m cx, m cy, m cz, Ixx, Iyy, Izz, Ixy, Iyz, Izx] (dynamics.py:225-230, loggers.py:133),

@@ -45,6 +45,7 @@ SIGNATURES = {
     "rbm_version": (C.c_char_p, []),
     "rbm_last_error_string": (C.c_char_p, []),
     "rbm_device_count": (C.c_int, []),
+    "rbm_device_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
     "rbm_model_create": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint, C.c_int, C.POINTER(_vp)]),
     "rbm_model_destroy": (None, [_vp]),
     "rbm_model_analyze": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint, C.POINTER(C.c_int), _vp, _vp]),
@@ -62,6 +63,11 @@ SIGNATURES = {
     "rbm_rnea_planned_f32": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double, _vp, _vp, _i64, _i64, _vp]),
     "rbm_rnea_host_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64]),
     "rbm_rnea_host_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i64]),
+    "rbm_model_live_inputs": (C.c_int, [_vp, _vp]),
+    "rbm_rnea_host_soa_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64]),
+    "rbm_rnea_host_soa_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64]),
+    "rbm_rnea_planned_host_f64": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double, _vp, _i64, _i64, _i64]),
+    "rbm_rnea_planned_host_f32": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double, _vp, _i64, _i64, _i64]),
     "rbm_regressor_rows_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rbm_sensor_twists_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "rbm_regressor_from_traj_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
@@ -97,15 +103,21 @@ def header_symbols():
 
 
 def load():
-    """Load (building in-tree first if the .so is missing or stale and nvcc exists) and type the library."""
+    """Load and type the library.  The in-tree build is refreshed first whenever it is missing or STALE: `build_library()` compares a
+    fingerprint of csrc/ + the header + the flags with the one recorded at the last build and returns at once when they match, so
+    an edited kernel can never run as an old binary.  Without nvcc a stale or missing library is an error (no fallback)."""
     global _lib
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH) or os.environ.get("RBM_REBUILD"):
-            from .build import build_library
+        from . import build as _build
 
-            build_library()
+        if _build.have_nvcc():
+            _build.build_library(force=bool(os.environ.get("RBM_REBUILD")))
+        elif not os.path.exists(LIB_PATH):
+            raise RbmError(f"{LIB_PATH} is missing and nvcc is not available to build it")
+        elif not _build.is_fresh():
+            raise RbmError(f"{LIB_PATH} is stale (csrc/ changed since it was built) and nvcc is not available to rebuild it")
         try:
             lib = C.CDLL(LIB_PATH)
         except OSError as e:  # no silent fallback

@@ -38,6 +38,16 @@ def _nvcc() -> str:
     return exe
 
 
+def have_nvcc() -> bool:
+    return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+
+
+def is_fresh() -> bool:
+    """True when librbm_b200.so exists and was built from the sources and flags that are in the tree now."""
+    stamp = os.path.join(OBJ, "fingerprint")
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == _fingerprint()
+
+
 def _sources():
     return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 

@@ -121,8 +121,49 @@ static void convert_fast(const FastParams<double>& a, FastParams<T>* b) {
 
 }  // namespace rbm
 
-// ---- host end-to-end path ---------------------------------------------------------------------
+// ---- host end-to-end paths ---------------------------------------------------------------------
+// Three-slot pipeline shared by the *_host entry points: slot k owns a stream and a device staging pair (in, out); chunk i runs
+// H2D -> kernel -> D2H on stream (i % 3), so the upload of one chunk, the kernel of the previous and the download of the one
+// before overlap.  One cudaMemcpyAsync / cudaMemcpy2DAsync per array and chunk (no batched-memcpy API).
 namespace rbm {
+
+static int ensure_pipe(const rbm_model* m, size_t in_bytes, size_t out_bytes) {
+  constexpr int kSlots = rbm_model::kPipeSlots;
+  for (int k = 0; k < kSlots; ++k)
+    if (!m->pipe_st[k]) RBM_CUDA_TRY(cudaStreamCreateWithFlags(&m->pipe_st[k], cudaStreamNonBlocking));
+  if (in_bytes > m->pipe_in_bytes || out_bytes > m->pipe_out_bytes) {
+    if (in_bytes < m->pipe_in_bytes) in_bytes = m->pipe_in_bytes;
+    if (out_bytes < m->pipe_out_bytes) out_bytes = m->pipe_out_bytes;
+    for (int k = 0; k < kSlots; ++k) {
+      RBM_CUDA_TRY(cudaStreamSynchronize(m->pipe_st[k]));
+      if (m->pipe_in[k]) cudaFree(m->pipe_in[k]);
+      if (m->pipe_out[k]) cudaFree(m->pipe_out[k]);
+      m->pipe_in[k] = m->pipe_out[k] = nullptr;
+    }
+    m->pipe_in_bytes = m->pipe_out_bytes = 0;
+    for (int k = 0; k < kSlots; ++k) {
+      RBM_CUDA_TRY(cudaMalloc(&m->pipe_in[k], in_bytes ? in_bytes : 16));
+      RBM_CUDA_TRY(cudaMalloc(&m->pipe_out[k], out_bytes ? out_bytes : 16));
+      // rows that a kernel path never reads are never uploaded either (rbm_rnea_host_soa_*): keep them defined
+      RBM_CUDA_TRY(cudaMemsetAsync(m->pipe_in[k], 0, in_bytes ? in_bytes : 16, m->pipe_st[k]));
+    }
+    m->pipe_in_bytes = in_bytes;
+    m->pipe_out_bytes = out_bytes;
+  }
+  return RBM_OK;
+}
+
+// drains the pipeline; on any failure the streams are drained BEFORE returning: copies of earlier chunks may still be reading the
+// caller's input / writing its output, and the caller may release those buffers as soon as the entry point returns
+static int drain_pipe(const rbm_model* m, int rc, const char* who) {
+  for (int k = 0; k < rbm_model::kPipeSlots; ++k) {
+    if (!m->pipe_st[k]) continue;
+    cudaError_t e = cudaStreamSynchronize(m->pipe_st[k]);
+    if (e != cudaSuccess && rc == RBM_OK) rc = cuda_fail(e, who);
+  }
+  return rc;
+}
+
 template <class T>
 int rnea_host(const rbm_model* m, const T* traj_host, T* tau_host, int64_t n, int64_t chunk) {
   if (!m) return invalid("rbm_rnea_host: model is NULL");
@@ -136,38 +177,111 @@ int rnea_host(const rbm_model* m, const T* traj_host, T* tau_host, int64_t n, in
   RBM_CUDA_TRY(guard.status());
   std::lock_guard<std::mutex> lock(m->pipe_mu);
   constexpr int kSlots = rbm_model::kPipeSlots;
-  const size_t in_bytes = sizeof(T) * chunk * 3 * nj, out_bytes = sizeof(T) * chunk * nj;
-  for (int k = 0; k < kSlots; ++k)
-    if (!m->pipe_st[k]) RBM_CUDA_TRY(cudaStreamCreateWithFlags(&m->pipe_st[k], cudaStreamNonBlocking));
-  if (in_bytes > m->pipe_in_bytes || out_bytes > m->pipe_out_bytes) {
-    for (int k = 0; k < kSlots; ++k) {
-      RBM_CUDA_TRY(cudaStreamSynchronize(m->pipe_st[k]));
-      if (m->pipe_in[k]) cudaFree(m->pipe_in[k]);
-      if (m->pipe_out[k]) cudaFree(m->pipe_out[k]);
-      m->pipe_in[k] = m->pipe_out[k] = nullptr;
-    }
-    m->pipe_in_bytes = m->pipe_out_bytes = 0;
-    for (int k = 0; k < kSlots; ++k) {
-      RBM_CUDA_TRY(cudaMalloc(&m->pipe_in[k], in_bytes));
-      RBM_CUDA_TRY(cudaMalloc(&m->pipe_out[k], out_bytes));
-    }
-    m->pipe_in_bytes = in_bytes;
-    m->pipe_out_bytes = out_bytes;
-  }
+  if (int rc0 = ensure_pipe(m, sizeof(T) * chunk * 3 * nj, sizeof(T) * chunk * nj)) return rc0;
+  int rc = RBM_OK;
   int slot = 0;
-  for (int64_t s0 = 0; s0 < n; s0 += chunk, slot = (slot + 1) % kSlots) {
+  for (int64_t s0 = 0; s0 < n && rc == RBM_OK; s0 += chunk, slot = (slot + 1) % kSlots) {
     const int64_t cnt = (n - s0 < chunk) ? (n - s0) : chunk;
     cudaStream_t st = m->pipe_st[slot];
     T* d_in = static_cast<T*>(m->pipe_in[slot]);
     T* d_out = static_cast<T*>(m->pipe_out[slot]);
     // stream order makes the slot safe to reuse: its previous D2H precedes this H2D on the same stream
-    RBM_CUDA_TRY(cudaMemcpyAsync(d_in, traj_host + s0 * 3 * nj, sizeof(T) * cnt * 3 * nj, cudaMemcpyHostToDevice, st));
-    int rc = launch_rnea_aos<T>(m, d_in, d_out, cnt, st);
-    if (rc != RBM_OK) return rc;
-    RBM_CUDA_TRY(cudaMemcpyAsync(tau_host + s0 * nj, d_out, sizeof(T) * cnt * nj, cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaMemcpyAsync(d_in, traj_host + s0 * 3 * nj, sizeof(T) * cnt * 3 * nj, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "rbm_rnea_host (H2D)"); break; }
+    rc = launch_rnea_aos<T>(m, d_in, d_out, cnt, st);
+    if (rc != RBM_OK) break;
+    e = cudaMemcpyAsync(tau_host + s0 * nj, d_out, sizeof(T) * cnt * nj, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "rbm_rnea_host (D2H)"); break; }
   }
-  for (int k = 0; k < kSlots; ++k) RBM_CUDA_TRY(cudaStreamSynchronize(m->pipe_st[k]));
-  return RBM_OK;
+  return drain_pipe(m, rc, "rbm_rnea_host (synchronize)");
+}
+
+// which rows of (q, qd, qdd) the inverse-dynamics kernel of this model reads: [3][nj], 1 = live
+static void live_inputs(const rbm_model* m, int32_t* mask) {
+  for (int i = 0; i < 3 * m->nj; ++i) mask[i] = 1;
+  // sequential structure (SequentialDesc::q_matters): tau, V_6 and dV_6 do not depend on the three gantry positions
+  if (m->path != PATH_GENERIC)
+    for (int j = 0; j < 3; ++j) mask[j] = 0;
+}
+
+// SoA host entry: q, qd, qdd [nj][ld] on the host -> tau [nj][ld] on the host.  Dead rows stay on the host.
+template <class T>
+int rnea_host_soa(const rbm_model* m, const T* q_host, const T* qd_host, const T* qdd_host, T* tau_host, int64_t n, int64_t ld, int64_t chunk) {
+  if (!m) return invalid("rbm_rnea_host_soa: model is NULL");
+  if (n < 0) return invalid("rbm_rnea_host_soa: n < 0");
+  if (n == 0) return RBM_OK;
+  if (!q_host || !qd_host || !qdd_host || !tau_host) return invalid("rbm_rnea_host_soa: NULL buffer");
+  if (ld < n) return invalid("rbm_rnea_host_soa: ld < n");
+  const int nj = m->nj;
+  if (chunk <= 0) chunk = 1 << 17;
+  if (chunk > n) chunk = n;
+  chunk = (chunk + 1) & ~int64_t(1);  // even device pitch: keeps the fp32 two-samples-per-thread kernel eligible
+  DeviceGuard guard(m->device);
+  RBM_CUDA_TRY(guard.status());
+  std::lock_guard<std::mutex> lock(m->pipe_mu);
+  constexpr int kSlots = rbm_model::kPipeSlots;
+  if (int rc0 = ensure_pipe(m, sizeof(T) * chunk * 3 * nj, sizeof(T) * chunk * nj)) return rc0;
+  int32_t live[3 * RBM_MAX_JOINTS];
+  live_inputs(m, live);
+  const T* src[3] = {q_host, qd_host, qdd_host};
+  int rc = RBM_OK;
+  int slot = 0;
+  for (int64_t s0 = 0; s0 < n && rc == RBM_OK; s0 += chunk, slot = (slot + 1) % kSlots) {
+    const int64_t cnt = (n - s0 < chunk) ? (n - s0) : chunk;
+    cudaStream_t st = m->pipe_st[slot];
+    T* d_in = static_cast<T*>(m->pipe_in[slot]);   // [3][nj][chunk]
+    T* d_out = static_cast<T*>(m->pipe_out[slot]); // [nj][chunk]
+    for (int a = 0; a < 3 && rc == RBM_OK; ++a) {
+      // maximal runs of live rows of array a: one strided 2-D copy each (row = cnt samples, host pitch ld, device pitch chunk)
+      for (int j = 0; j < nj;) {
+        if (!live[a * nj + j]) { ++j; continue; }
+        int j1 = j;
+        while (j1 < nj && live[a * nj + j1]) ++j1;
+        cudaError_t e = cudaMemcpy2DAsync(d_in + ((int64_t)a * nj + j) * chunk, sizeof(T) * chunk, src[a] + (int64_t)j * ld + s0, sizeof(T) * ld,
+                                          sizeof(T) * cnt, (size_t)(j1 - j), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "rbm_rnea_host_soa (H2D)"); break; }
+        j = j1;
+      }
+    }
+    if (rc != RBM_OK) break;
+    rc = launch_rnea_soa<T>(m, d_in, d_in + (int64_t)nj * chunk, d_in + (int64_t)2 * nj * chunk, d_out, nullptr, nullptr, cnt, chunk, st);
+    if (rc != RBM_OK) break;
+    cudaError_t e = cudaMemcpy2DAsync(tau_host + s0, sizeof(T) * ld, d_out, sizeof(T) * chunk, sizeof(T) * cnt, (size_t)nj, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "rbm_rnea_host_soa (D2H)"); break; }
+  }
+  return drain_pipe(m, rc, "rbm_rnea_host_soa (synchronize)");
+}
+
+// planner-driven host entry: nothing uploaded, tau [nj][ld] downloaded
+template <class T>
+int rnea_planned_host(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double timestep, double step0, double stride,
+                      T* tau_host, int64_t n, int64_t ld, int64_t chunk) {
+  if (!m) return invalid("rbm_rnea_planned_host: model is NULL");
+  if (n < 0) return invalid("rbm_rnea_planned_host: n < 0");
+  if (n == 0) return RBM_OK;
+  if (!coeffs || !disp || !offset || !tau_host) return invalid("rbm_rnea_planned_host: NULL pointer");
+  if (ld < n) return invalid("rbm_rnea_planned_host: ld < n");
+  if (!(timestep > 0.0)) return invalid("rbm_rnea_planned_host: timestep must be positive");
+  const int nj = m->nj;
+  if (chunk <= 0) chunk = 1 << 17;
+  if (chunk > n) chunk = n;
+  DeviceGuard guard(m->device);
+  RBM_CUDA_TRY(guard.status());
+  std::lock_guard<std::mutex> lock(m->pipe_mu);
+  constexpr int kSlots = rbm_model::kPipeSlots;
+  if (int rc0 = ensure_pipe(m, 0, sizeof(T) * chunk * nj)) return rc0;
+  int rc = RBM_OK;
+  int slot = 0;
+  for (int64_t s0 = 0; s0 < n && rc == RBM_OK; s0 += chunk, slot = (slot + 1) % kSlots) {
+    const int64_t cnt = (n - s0 < chunk) ? (n - s0) : chunk;
+    cudaStream_t st = m->pipe_st[slot];
+    T* d_out = static_cast<T*>(m->pipe_out[slot]);
+    rc = launch_rnea_planned<T>(m, coeffs, disp, offset, timestep, step0 + (double)s0 * stride, stride, d_out, nullptr, cnt, chunk, st);
+    if (rc != RBM_OK) break;
+    cudaError_t e = cudaMemcpy2DAsync(tau_host + s0, sizeof(T) * ld, d_out, sizeof(T) * chunk, sizeof(T) * cnt, (size_t)nj, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "rbm_rnea_planned_host (D2H)"); break; }
+  }
+  return drain_pipe(m, rc, "rbm_rnea_planned_host (synchronize)");
 }
 }  // namespace rbm
 
@@ -178,6 +292,12 @@ extern "C" {
 
 const char* rbm_version(void) { return "rbm_b200 0.1 (sm_100a)"; }
 const char* rbm_last_error_string(void) { return g_last_error.c_str(); }
+
+int rbm_device_pci_bus_id(int device, char* out, int len) {
+  if (!out || len < 13) return invalid("rbm_device_pci_bus_id: need a buffer of at least 13 bytes");
+  RBM_CUDA_TRY(cudaDeviceGetPCIBusId(out, len, device));
+  return RBM_OK;
+}
 
 int rbm_device_count(void) {
   int n = 0;
@@ -390,6 +510,28 @@ int rbm_rnea_host_f64(const rbm_model* m, const double* traj_host, double* tau_h
 }
 int rbm_rnea_host_f32(const rbm_model* m, const float* traj_host, float* tau_host, int64_t n, int64_t chunk) {
   return rnea_host<float>(m, traj_host, tau_host, n, chunk);
+}
+
+int rbm_rnea_host_soa_f64(const rbm_model* m, const double* q_host, const double* qd_host, const double* qdd_host, double* tau_host, int64_t n,
+                          int64_t ld, int64_t chunk) {
+  return rnea_host_soa<double>(m, q_host, qd_host, qdd_host, tau_host, n, ld, chunk);
+}
+int rbm_rnea_host_soa_f32(const rbm_model* m, const float* q_host, const float* qd_host, const float* qdd_host, float* tau_host, int64_t n, int64_t ld,
+                          int64_t chunk) {
+  return rnea_host_soa<float>(m, q_host, qd_host, qdd_host, tau_host, n, ld, chunk);
+}
+int rbm_rnea_planned_host_f64(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double timestep, double step0,
+                              double stride, double* tau_host, int64_t n, int64_t ld, int64_t chunk) {
+  return rnea_planned_host<double>(m, coeffs, disp, offset, timestep, step0, stride, tau_host, n, ld, chunk);
+}
+int rbm_rnea_planned_host_f32(const rbm_model* m, const double* coeffs, const double* disp, const double* offset, double timestep, double step0,
+                              double stride, float* tau_host, int64_t n, int64_t ld, int64_t chunk) {
+  return rnea_planned_host<float>(m, coeffs, disp, offset, timestep, step0, stride, tau_host, n, ld, chunk);
+}
+int rbm_model_live_inputs(const rbm_model* m, int32_t* mask) {
+  if (!m || !mask) return invalid("rbm_model_live_inputs: NULL argument");
+  live_inputs(m, mask);
+  return RBM_OK;
 }
 
 

@@ -92,7 +92,9 @@ struct GenericEval {
     T qdd0[MAXJ];
 #pragma unroll
     for (int k = 0; k < MAXJ; ++k) qdd0[k] = T(0);
-    generic_rnea<T, 0>(sp, zero, nj_, q, qd, qdd0, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
+    // full base (twist_0, dtwist_0, tip wrench): with a moving base d tau / d qd contains V_0 x (S qd) coupling terms, so the base
+    // twist must stay on; the gravity / tip-wrench parts are the same in every evaluation and cancel in the finite differences
+    generic_rnea<T, 0>(sp, sp, nj_, q, qd, qdd0, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
   }
   RBM_HD void id_inertia(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qdd)[MAXJ], T (&tau)[MAXJ]) const {
     T qd0[MAXJ];

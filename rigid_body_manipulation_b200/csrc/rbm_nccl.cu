@@ -7,6 +7,7 @@
 // rigid_body_manipulation_b200/distributed.py).
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "rbm_internal.h"
@@ -31,13 +32,19 @@ struct NcclApi {
 NcclApi& api() {
   static NcclApi a = [] {
     NcclApi x;
+    const char* override_name = getenv("RBM_NCCL_LIB");  // e.g. a path that does not exist: exercises the NCCL-less behaviour
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* n : names) {
-      x.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-      if (x.handle) break;
+    if (override_name && override_name[0]) {
+      x.handle = dlopen(override_name, RTLD_NOW | RTLD_GLOBAL);
+    } else {
+      for (const char* n : names) {
+        x.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (x.handle) break;
+      }
     }
     if (!x.handle) {
-      x.error = std::string("cannot dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "unknown");
+      const char* e = dlerror();  // one call: dlerror() clears the message it returns
+      x.error = std::string("cannot dlopen libnccl.so.2: ") + (e ? e : "unknown");
       return x;
     }
     auto sym = [&](const char* s) { return dlsym(x.handle, s); };

@@ -9,6 +9,9 @@
 // non-zero entries of the two diagonal blocks in registers, blocks reduce with warp shuffles + shared
 // memory, and a second single-block kernel sums the per-block partials in a FIXED order (deterministic
 // result for a given grid).  HBM traffic per sample: q, qd, qdd, f = 24 scalars read, nothing written.
+#include <atomic>
+#include <cstdlib>
+
 #include "rbm_async.cuh"
 #include "rbm_internal.h"
 #include "rbm_gram.cuh"
@@ -354,6 +357,189 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
   gram_block_epilogue<T>(acc, red, partials);
 }
 
+// ---- software-pipelined variant (round 2; the production kernel of the fast paths) ---------------------------------------------
+// Two changes against k_regressor_gram_tma, both from the round-1 ncu reading (FP64 pipe ~60 % busy at 2 warps per scheduler, stalls
+// on fixed-latency dependencies; 1.14x the needed DRAM traffic):
+//   * only the LIVE streams are staged.  V_6 and dV_6 of the sequential structure do not depend on the three gantry positions
+//     (SequentialDesc::q_matters), so q[0..2] are never read: 21 bulk copies per tile instead of 24, 168 instead of 192 B of DRAM
+//     traffic per fp64 sample, and the smaller tile buys a fifth stage.
+//   * the accumulation of sample i is issued together with the kinematics of sample i + 1.  The kinematic chain (three sincos, six
+//     links) is one long dependent sequence and the 180 accumulation FMAs are mutually independent, but inside one sample the second
+//     needs the end of the first; carrying (x, w, dw, f) -- 15 scalars -- over one iteration puts both in the same basic block, so
+//     each warp fills its own chain bubbles instead of relying on the one other warp of its scheduler.
+// The sums are the same terms in the same order as before: results are bit-identical to k_regressor_gram_tma.
+constexpr int kLiveStreams = 21;  // q3..5 (3) | qd (6) | qdd (6) | f (6)
+constexpr int kPipeStages = 5;
+
+template <class T>
+struct GramCarry {
+  T x[3], w[3], l[3], f[6];
+};
+
+// accumulation half
+template <class T>
+__device__ __forceinline__ void gram_accumulate_carry(T (&acc)[kAcc], const GramCarry<T>& z) {
+  T top[3][4], bot[3][9];
+  regressor_blocks_xwl(z.x, z.w, z.l, top, bot);
+  gram_accumulate(acc, top, bot, z.f);
+}
+
+// kinematics half: (q, qd, qdd) and the joint sines / cosines -> sensor-frame (x = dv + w x v, w, dw)
+template <class T, int PATH, bool SEN_DIAG>
+__device__ __forceinline__ void gram_kinematics_cs(const FastParams<T>& P, const T (&rq)[6], const T (&c)[6], const T (&s)[6], const T (&rqd)[6],
+                                                   const T (&rqdd)[6], GramCarry<T>& z) {
+  FastResult<T> r;
+  if constexpr (PATH == PATH_SEQ_ISO) fast_rnea_cs<T, SeqIso, false>(P, rq, c, s, rqd, rqdd, r);
+  else fast_rnea_cs<T, SeqRigid, false>(P, rq, c, s, rqd, rqdd, r);
+  T V[6], dV[6], Vs[6], dVs[6];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { V[k] = r.v[k]; V[3 + k] = r.w[k]; dV[k] = r.a[k]; dV[3 + k] = r.l[k]; }
+  if constexpr (SEN_DIAG) {  // Ad(T) is a component-wise sign pattern (the reference's F/T site: Rz(180 deg), no offset)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const T d = P.senR[4 * k];
+      Vs[k] = d * V[k]; Vs[3 + k] = d * V[3 + k];
+      dVs[k] = d * dV[k]; dVs[3 + k] = d * dV[3 + k];
+    }
+  } else {
+    sensor_twists(P.senR, P.sent, V, dV, Vs, dVs);
+  }
+  regressor_x(Vs, dVs, z.x);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { z.w[k] = Vs[3 + k]; z.l[k] = dVs[3 + k]; }
+}
+
+// One pipelined step: kinematics of the current sample (into zn) TOGETHER with the accumulation of the previous one (z).  The
+// branch on the trigonometric fast range comes FIRST and each arm holds the whole step, so that in the (always taken) fast arm the
+// dependent chain -- range reduction, polynomials, six links -- and the 180 independent accumulation FMAs are ONE basic block for
+// ptxas to interleave.  (With the usual "if (ok) fast else lib; then the rest" shape the chain is cut into blocks and the
+// accumulation is scheduled after it: verified in the SASS.)
+template <class T, int PATH, bool SEN_DIAG>
+__device__ __forceinline__ void gram_step(const FastParams<T>& P, const T (&rq)[6], const T (&rqd)[6], const T (&rqdd)[6], GramCarry<T>& zn,
+                                          const GramCarry<T>& z, T (&acc)[kAcc]) {
+  T c[6], s[6];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { c[i] = T(1); s[i] = T(0); }
+  if (trig_fast_ok(rq[3]) && trig_fast_ok(rq[4]) && trig_fast_ok(rq[5])) {
+#pragma unroll
+    for (int i = 3; i < 6; ++i) sincos_core(rq[i], s[i], c[i]);
+    gram_kinematics_cs<T, PATH, SEN_DIAG>(P, rq, c, s, rqd, rqdd, zn);
+    gram_accumulate_carry(acc, z);
+  } else {
+#pragma unroll
+    for (int i = 3; i < 6; ++i) sincos_lib(rq[i], &s[i], &c[i]);
+    gram_kinematics_cs<T, PATH, SEN_DIAG>(P, rq, c, s, rqd, rqdd, zn);
+    gram_accumulate_carry(acc, z);
+  }
+}
+
+template <class T>
+__device__ __forceinline__ const T* live_stream(int k, const T* q, const T* qd, const T* qdd, const T* f, int64_t ld) {
+  return k < 3 ? q + (int64_t)(3 + k) * ld : k < 9 ? qd + (int64_t)(k - 3) * ld : k < 15 ? qdd + (int64_t)(k - 9) * ld : f + (int64_t)(k - 15) * ld;
+}
+
+template <class T, int PATH, bool SEN_DIAG>
+__global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regressor_gram_pipe(const __grid_constant__ FastParams<T> P, const T* __restrict__ q,
+                                                                                             const T* __restrict__ qd, const T* __restrict__ qdd,
+                                                                                             const T* __restrict__ f, double* __restrict__ partials,
+                                                                                             int64_t n, int64_t ld) {
+  constexpr int S = kPipeStages;
+  constexpr int NW = kGramBlock / 32;
+  constexpr uint32_t kRowBytes = kGramBlock * sizeof(T);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* buf = reinterpret_cast<T*>(smem_raw);  // [S][kLiveStreams][kGramBlock]
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ double red[NW][kAcc];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t nfull = n / kGramBlock;  // tiles moved by bulk copies; a ragged tail tile is read directly
+  for (int k = lane; k < kAcc; k += 32) red[warp][k] = 0.0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], NW);  // one arrive.expect_tx per warp (its share of the 21 copies)
+    mbar_init_fence();
+  }
+  __syncthreads();
+
+  // The issue cost of a bulk copy is paid by the issuing warp: lane 0 of warp w brings streams w, w + 8, w + 16 (< 21).
+  const int my_copies = (warp + 16 < kLiveStreams) ? 3 : 2;
+  auto issue = [&](int64_t it) {
+    const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= nfull) return;
+    const int st = (int)(it % S);
+    uint64_t* bar = &full[st];
+    mbar_arrive_expect_tx(bar, my_copies * kRowBytes);
+    T* dst = buf + (size_t)st * kLiveStreams * kGramBlock;
+    const int64_t s0 = tile * kGramBlock;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k = warp + NW * i;
+      if (k < kLiveStreams) bulk_copy_g2s(dst + k * kGramBlock, live_stream(k, q, qd, qdd, f, ld) + s0, kRowBytes, bar);
+    }
+  };
+  if (lane == 0) {
+    for (int it = 0; it < S; ++it) issue(it);
+  }
+
+  T acc[kAcc];
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[k] = T(0);
+  GramCarry<T> z;  // the previous sample, not yet accumulated (zeros: accumulating them adds exact zeros)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { z.x[k] = T(0); z.w[k] = T(0); z.l[k] = T(0); z.f[k] = T(0); z.f[3 + k] = T(0); }
+  int since_flush = -1;  // the first accumulation is the all-zero carry and does not count
+  for (int64_t it = 0;; ++it) {
+    const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= nfull) break;
+    const int st = (int)(it % S);
+    mbar_wait(&full[st], (uint32_t)((it / S) & 1));
+    const T* src = buf + (size_t)st * kLiveStreams * kGramBlock + tid;
+    T rq[6], rqd[6], rqdd[6];
+    GramCarry<T> zn;
+    rq[0] = rq[1] = rq[2] = T(0);  // dead inputs of the sequential structure
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rq[3 + k] = src[k * kGramBlock];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      rqd[k] = src[(3 + k) * kGramBlock];
+      rqdd[k] = src[(9 + k) * kGramBlock];
+      zn.f[k] = src[(15 + k) * kGramBlock];
+    }
+    __syncthreads();               // every thread holds its sample in registers: the stage can be refilled
+    if (lane == 0) issue(it + S);  // each warp re-issues its streams
+    gram_step<T, PATH, SEN_DIAG>(P, rq, rqd, rqdd, zn, z, acc);
+    z = zn;
+    if constexpr (sizeof(T) == 4) {
+      if (++since_flush == kFlush) {
+        since_flush = 0;
+        gram_flush_f32(acc, red[warp], lane);
+      }
+    }
+  }
+  gram_accumulate_carry(acc, z);
+  // ragged tail (n % 256 samples): owned by the CTA that would have received tile `nfull`
+  if ((nfull % gridDim.x) == blockIdx.x) {
+    const int64_t s = nfull * kGramBlock + tid;
+    if (s < n) {
+      T rq[6], rqd[6], rqdd[6];
+      rq[0] = rq[1] = rq[2] = T(0);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) rq[3 + k] = __ldg(q + (3 + k) * ld + s);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        rqd[k] = __ldg(qd + k * ld + s);
+        rqdd[k] = __ldg(qdd + k * ld + s);
+        z.f[k] = __ldg(f + k * ld + s);
+      }
+      GramCarry<T> none = z;  // accumulated right below, in the same step as its own kinematics would be for the NEXT sample
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { none.x[k] = T(0); none.w[k] = T(0); none.l[k] = T(0); none.f[k] = T(0); none.f[3 + k] = T(0); }
+      gram_step<T, PATH, SEN_DIAG>(P, rq, rqd, rqdd, z, none, acc);
+      gram_accumulate_carry(acc, z);
+    }
+  }
+  gram_block_epilogue<T>(acc, red, partials);
+}
+
 // partials [nblocks][70] -> pack [112] = [Y^T Y (100, row-major) | Y^T f (10) | f^T f | n]
 __global__ void __launch_bounds__(128) k_gram_finalize(const double* __restrict__ partials, int nblocks, double n_samples, double* __restrict__ pack) {
   __shared__ double tot[kAcc];
@@ -481,6 +667,15 @@ int launch_regressor_gram_grouped(const rbm_model* m, const T* q, const T* qd, c
 template int launch_regressor_gram_grouped<double>(const rbm_model*, const double*, const double*, const double*, const double*, int64_t, int64_t, int64_t, double*,
                                                    int64_t, int64_t, int64_t, cudaStream_t);
 
+// development knob: RBM_GRAM_VARIANT=0 selects the round-1 TMA kernel (24 streams, no software pipelining) for A/B timing
+static int gram_variant() {
+  static const int v = [] {
+    const char* e = getenv("RBM_GRAM_VARIANT");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+
 template <class T>
 int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* qdd, const T* f, double* pack, double* partials, int64_t n, int64_t ld,
                           cudaStream_t st) {
@@ -493,18 +688,38 @@ int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* 
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const bool tma_ok = m->path != PATH_GENERIC && al16(q) && al16(qd) && al16(qdd) && al16(f) && ((ld * sizeof(T)) % 16 == 0) && n >= kGramBlock &&
                         !m->no_tma;
-    if (tma_ok) {
+    if (tma_ok && gram_variant() == 0) {  // round-1 kernel, kept for A/B runs (RBM_GRAM_VARIANT=0)
       grid = gram_grid(m, n, sizeof(T) == 4 ? 2 : 1);  // fp32: 119 registers, 96 KB of stages: two CTAs per SM
       constexpr size_t smem = (size_t)kGramStages * kStreams * kGramBlock * sizeof(T);
-      static bool attr_set[64] = {false};  // function attributes are per device; idempotent, so a benign race at worst
+      static std::atomic<bool> attr_set[64];  // function attributes are per device
       const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
-      if (!attr_set[dev]) {
+      if (!attr_set[dev].load(std::memory_order_acquire)) {
         RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_tma<T, PATH_SEQ_ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_tma<T, PATH_SEQ_RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[dev] = true;
+        attr_set[dev].store(true, std::memory_order_release);
       }
       if (m->path == PATH_SEQ_ISO) k_regressor_gram_tma<T, PATH_SEQ_ISO><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
       else k_regressor_gram_tma<T, PATH_SEQ_RIGID><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
+    } else if (tma_ok) {
+      grid = gram_grid(m, n, sizeof(T) == 4 ? 2 : 1);  // fp32: two CTAs per SM (105 KB of stages each)
+      constexpr size_t smem = (size_t)kPipeStages * kLiveStreams * kGramBlock * sizeof(T);
+      static std::atomic<bool> attr_set[64];
+      const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
+      if (!attr_set[dev].load(std::memory_order_acquire)) {
+        RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_pipe<T, PATH_SEQ_ISO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_pipe<T, PATH_SEQ_RIGID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_pipe<T, PATH_SEQ_ISO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_pipe<T, PATH_SEQ_RIGID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev].store(true, std::memory_order_release);
+      }
+      const bool diag = P.sen_diag != T(0);
+      if (m->path == PATH_SEQ_ISO) {
+        if (diag) k_regressor_gram_pipe<T, PATH_SEQ_ISO, true><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
+        else k_regressor_gram_pipe<T, PATH_SEQ_ISO, false><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
+      } else {
+        if (diag) k_regressor_gram_pipe<T, PATH_SEQ_RIGID, true><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
+        else k_regressor_gram_pipe<T, PATH_SEQ_RIGID, false><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
+      }
     } else if (m->path == PATH_SEQ_ISO) {
       k_regressor_gram<T, PATH_SEQ_ISO><<<grid, kGramBlock, 0, st>>>(P, gp, m->nj, np, q, qd, qdd, f, partials, n, ld);
     } else if (m->path == PATH_SEQ_RIGID) {

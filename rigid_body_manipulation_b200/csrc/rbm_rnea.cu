@@ -3,6 +3,7 @@
 // One sample per thread; consecutive threads own consecutive samples, so every SoA stream
 // (q_j, qd_j, qdd_j, tau_j) is read / written as fully coalesced 128-byte lines and nothing is
 // re-read: HBM traffic == algorithmic traffic == 24 * sizeof(T) bytes per sample.
+#include <atomic>
 #include <cstdlib>
 
 #include "rbm_async.cuh"
@@ -413,12 +414,12 @@ int launch_rnea_aos(const rbm_model* m, const T* traj, T* tau, int64_t n, cudaSt
   const bool aligned = ((reinterpret_cast<uintptr_t>(traj) | reinterpret_cast<uintptr_t>(tau)) & 15u) == 0;
   if (m->path != PATH_GENERIC && aligned && !m->no_tma && n >= kBlock) {
     constexpr size_t smem = ((size_t)kAosStages * 18 + 2 * 6) * kBlock * sizeof(T);
-    static bool attr_set[64] = {false};
+    static std::atomic<bool> attr_set[64];  // function attributes are per device; set once per device
     const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
-    if (!attr_set[dev]) {
+    if (!attr_set[dev].load(std::memory_order_acquire)) {
       RBM_CUDA_TRY(cudaFuncSetAttribute(k_rnea_fast_aos_tma<T, SeqIso>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       RBM_CUDA_TRY(cudaFuncSetAttribute(k_rnea_fast_aos_tma<T, SeqRigid>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set[dev] = true;
+      attr_set[dev].store(true, std::memory_order_release);
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);

@@ -429,11 +429,19 @@ RBM_HD void sensor_twists(const T* R, const T* t, const T* V, const T* dV, T* Vs
 
 // Non-zero blocks of the 6x10 regressor:  top (rows 0-2, cols 0-3) = [x | [dw]x + [w]x[w]x],
 // bot (rows 3-5, cols 1-9) = [-[x]x | bullet(dw) + [w]x bullet(w)]   with x = dv + w x v.
+// Two stages so that the Gram kernels can carry just (x, w, dw) -- 9 scalars -- from one sample to the next.
 template <class T>
-RBM_HD void regressor_blocks(const T* V, const T* dV, T (&top)[3][4], T (&bot)[3][9]) {
+RBM_HD void regressor_x(const T* V, const T* dV, T (&x)[3]) {
   const T vx = V[0], vy = V[1], vz = V[2], wx = V[3], wy = V[4], wz = V[5];
-  const T ax = dV[0], ay = dV[1], az = dV[2], lx = dV[3], ly = dV[4], lz = dV[5];
-  const T x0 = ax + (wy * vz - wz * vy), x1 = ay + (wz * vx - wx * vz), x2 = az + (wx * vy - wy * vx);
+  x[0] = dV[0] + (wy * vz - wz * vy);
+  x[1] = dV[1] + (wz * vx - wx * vz);
+  x[2] = dV[2] + (wx * vy - wy * vx);
+}
+template <class T>
+RBM_HD void regressor_blocks_xwl(const T (&x)[3], const T* w, const T* l, T (&top)[3][4], T (&bot)[3][9]) {
+  const T wx = w[0], wy = w[1], wz = w[2];
+  const T lx = l[0], ly = l[1], lz = l[2];
+  const T x0 = x[0], x1 = x[1], x2 = x[2];
   const T xx = wx * wx, yy = wy * wy, zz = wz * wz, xy = wx * wy, yz = wy * wz, zx = wz * wx;
   top[0][0] = x0; top[0][1] = -(yy + zz); top[0][2] = xy - lz;     top[0][3] = zx + ly;
   top[1][0] = x1; top[1][1] = xy + lz;    top[1][2] = -(xx + zz);  top[1][3] = yz - lx;
@@ -446,6 +454,12 @@ RBM_HD void regressor_blocks(const T* V, const T* dV, T (&top)[3][4], T (&bot)[3
   bot[0][3] = lx;   bot[0][4] = -yz;  bot[0][5] = yz;   bot[0][6] = ly - zx; bot[0][7] = yy - zz; bot[0][8] = lz + xy;
   bot[1][3] = zx;   bot[1][4] = ly;   bot[1][5] = -zx;  bot[1][6] = lx + yz; bot[1][7] = lz - xy; bot[1][8] = zz - xx;
   bot[2][3] = -xy;  bot[2][4] = xy;   bot[2][5] = lz;   bot[2][6] = xx - yy; bot[2][7] = ly + zx; bot[2][8] = lx - yz;
+}
+template <class T>
+RBM_HD void regressor_blocks(const T* V, const T* dV, T (&top)[3][4], T (&bot)[3][9]) {
+  T x[3];
+  regressor_x(V, dV, x);
+  regressor_blocks_xwl(x, V + 3, dV + 3, top, bot);
 }
 
 // ---- planner-driven inputs (planners/joint_position_planner.py:86-131): the quintic profile is evaluated in double in the step

@@ -160,6 +160,8 @@ class Model:
         n = traj.shape[0]
         if tau is None:
             tau = torch.empty((n, self.nj), dtype=traj.dtype, device=traj.device)
+        elif tuple(tau.shape) != (n, self.nj) or tau.dtype != traj.dtype:
+            raise ValueError(f"tau must have shape ({n}, {self.nj}) and the dtype of traj")
         fn = self._lib.rbm_rnea_aos_f64 if traj.dtype == torch.float64 else self._lib.rbm_rnea_aos_f32
         with torch.cuda.device(self.device):
             rc = fn(self._h, _ptr(traj), _ptr(tau), n, self._stream())
@@ -208,6 +210,8 @@ class Model:
             raise ValueError("dtype must be float64 or float32")
         if tau is None:
             tau = torch.empty((self.nj, n), dtype=dtype, device=self.device)
+        elif tuple(tau.shape) != (self.nj, n) or tau.dtype != dtype:
+            raise ValueError(f"tau must have shape ({self.nj}, {n}) and dtype {dtype}")
         self._check_dev(tau)
         traj = torch.empty((3, self.nj, n), dtype=dtype, device=self.device) if want_traj else None
         co = np.ascontiguousarray(plan.coeffs, dtype=np.float64)
@@ -220,23 +224,95 @@ class Model:
         return (tau, traj) if want_traj else tau
 
     # ---- host end-to-end ---------------------------------------------------------------------------
+    @staticmethod
+    def _host_array(a, what):
+        """(tensor-or-ndarray, is_tensor, numpy dtype) of a contiguous HOST buffer; raises for CUDA tensors / strided views."""
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                raise ValueError(f"{what} must live in host memory")
+            if not a.is_contiguous():
+                raise ValueError(f"{what} must be contiguous")
+            if a.dtype not in (torch.float64, torch.float32):
+                raise ValueError(f"{what} must be float64 or float32")
+            return a, True, np.dtype(np.float64 if a.dtype == torch.float64 else np.float32)
+        a = np.asarray(a)
+        if a.dtype not in (np.float64, np.float32) or not a.flags.c_contiguous:
+            raise ValueError(f"{what} must be a C-contiguous float64 / float32 array")
+        return a, False, a.dtype
+
     def rnea_host(self, traj, tau=None, chunk=0):
         """traj: HOST array / pinned CPU tensor (n, 3, nj); returns tau on the host (same kind).  H2D, kernel and D2H are
         pipelined inside the library (rbm_rnea_host_*)."""
-        is_t = isinstance(traj, torch.Tensor)
-        if is_t and traj.is_cuda:
-            raise ValueError("rnea_host takes host memory; use rnea_aos for device tensors")
-        arr = traj if is_t else np.ascontiguousarray(traj)
-        shape, dt = tuple(arr.shape), (arr.dtype if not is_t else {torch.float64: np.float64, torch.float32: np.float32}[arr.dtype])
+        if not isinstance(traj, torch.Tensor):
+            traj = np.ascontiguousarray(traj)
+        arr, is_t, dt = self._host_array(traj, "traj")
+        shape = tuple(arr.shape)
         if len(shape) != 3 or shape[1] != 3 or shape[2] != self.nj:
             raise ValueError(f"traj must have shape (n, 3, {self.nj})")
         n = shape[0]
         if tau is None:
             tau = torch.empty((n, self.nj), dtype=arr.dtype, pin_memory=True) if is_t else np.empty((n, self.nj), dtype=dt)
-        fn = self._lib.rbm_rnea_host_f64 if np.dtype(dt) == np.float64 else self._lib.rbm_rnea_host_f32
+        else:
+            tau, _, tdt = self._host_array(tau, "tau")
+            if tuple(tau.shape) != (n, self.nj) or tdt != dt:
+                raise ValueError(f"tau must be a host buffer of shape ({n}, {self.nj}) with the dtype of traj")
+        fn = self._lib.rbm_rnea_host_f64 if dt == np.float64 else self._lib.rbm_rnea_host_f32
         rc = fn(self._h, _ptr(arr), _ptr(tau), n, int(chunk))
         _lib.check(rc, "rbm_rnea_host")
         return tau
+
+    def rnea_host_soa(self, q, qd, qdd, tau=None, chunk=0):
+        """SoA host entry: q, qd, qdd HOST buffers (nj, n) -> tau (nj, n) on the host.  Only the rows the model's kernel path
+        actually reads cross the bus (`live_inputs()`: the sequential structure never reads the three gantry positions, so 15 of
+        the 18 input rows are uploaded), one cudaMemcpyAsync per live row and chunk, pipelined with the kernel and the D2H of tau."""
+        bufs = []
+        for name, a in (("q", q), ("qd", qd), ("qdd", qdd)):
+            arr, is_t, dt = self._host_array(a, name)
+            bufs.append((arr, is_t, dt))
+        (qa, is_t, dt) = bufs[0]
+        if qa.ndim != 2 or qa.shape[0] != self.nj or any(tuple(b[0].shape) != tuple(qa.shape) or b[2] != dt for b in bufs[1:]):
+            raise ValueError(f"q, qd, qdd must be host buffers of one dtype with shape ({self.nj}, n)")
+        n = qa.shape[1]
+        if tau is None:
+            tau = torch.empty((self.nj, n), dtype=qa.dtype, pin_memory=True) if is_t else np.empty((self.nj, n), dtype=dt)
+        else:
+            tau, _, tdt = self._host_array(tau, "tau")
+            if tuple(tau.shape) != (self.nj, n) or tdt != dt:
+                raise ValueError(f"tau must be a host buffer of shape ({self.nj}, {n}) with the dtype of q")
+        fn = self._lib.rbm_rnea_host_soa_f64 if dt == np.float64 else self._lib.rbm_rnea_host_soa_f32
+        rc = fn(self._h, _ptr(qa), _ptr(bufs[1][0]), _ptr(bufs[2][0]), _ptr(tau), n, n, int(chunk))
+        _lib.check(rc, "rbm_rnea_host_soa")
+        return tau
+
+    def rnea_planned_host(self, plan, n=None, step0=None, stride=1.0, dtype=torch.float64, tau=None, chunk=0):
+        """Planner-driven end to end: the trajectory is generated in the kernel, so nothing is uploaded and only tau (nj, n) comes
+        back to the host (pinned tensor), chunked so that the D2H of one chunk overlaps the kernel of the next."""
+        n = plan.n_steps if n is None else int(n)
+        step0 = float(plan.init_step if step0 is None else step0)
+        if len(plan.displacement) != self.nj or len(plan.pos_offset) != self.nj:
+            raise ValueError(f"plan must have {self.nj} joints")
+        if dtype not in (torch.float64, torch.float32):
+            raise ValueError("dtype must be float64 or float32")
+        if tau is None:
+            tau = torch.empty((self.nj, n), dtype=dtype, pin_memory=True)
+        else:
+            tau, _, tdt = self._host_array(tau, "tau")
+            if tuple(tau.shape) != (self.nj, n) or tdt != np.dtype(np.float64 if dtype == torch.float64 else np.float32):
+                raise ValueError(f"tau must be a host buffer of shape ({self.nj}, {n}) and dtype {dtype}")
+        co = np.ascontiguousarray(plan.coeffs, dtype=np.float64)
+        di = np.ascontiguousarray(plan.displacement, dtype=np.float64)
+        of = np.ascontiguousarray(plan.pos_offset, dtype=np.float64)
+        fn = self._lib.rbm_rnea_planned_host_f64 if dtype == torch.float64 else self._lib.rbm_rnea_planned_host_f32
+        rc = fn(self._h, _ptr(co), _ptr(di), _ptr(of), float(plan.timestep), step0, float(stride), _ptr(tau), n, n, int(chunk))
+        _lib.check(rc, "rbm_rnea_planned_host")
+        return tau
+
+    def live_inputs(self):
+        """Boolean mask (3, nj): which rows of (q, qd, qdd) the model's inverse-dynamics kernel reads (rbm_model_live_inputs)."""
+        mask = np.zeros(3 * self.nj, dtype=np.int32)
+        rc = self._lib.rbm_model_live_inputs(self._h, _ptr(mask))
+        _lib.check(rc, "rbm_model_live_inputs")
+        return mask.reshape(3, self.nj).astype(bool)
 
     # ---- sensor-frame regressor / identification --------------------------------------------------
     def _check_soa(self, *ts):

@@ -70,3 +70,25 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(src), f"{f} imports the oracle"
                 assert "/root/reference" not in src or f in ("extract_reference_assets.py",), f
+
+
+def test_nccl_less_machine_reports_unavailable_instead_of_crashing():
+    """with libnccl absent rbm_nccl_available() must return 0 (include/rbm_b200.h) and leave a message -- it used to
+    call dlerror() twice and build a std::string from NULL.  Fresh process: the binding is resolved once per process."""
+    import subprocess
+    import sys
+
+    code = (
+        "import ctypes, sys\n"
+        "from rigid_body_manipulation_b200 import _lib\n"
+        "lib = _lib.load()\n"
+        "ok = lib.rbm_nccl_available()\n"
+        "msg = _lib.last_error()\n"
+        "buf = (ctypes.c_ubyte * 128)()\n"
+        "rc = lib.rbm_nccl_unique_id(buf)\n"
+        "print(ok, rc, msg)\n"
+        "sys.exit(0 if (ok == 0 and rc == _lib.RBM_ERR_NCCL and 'dlopen' in msg) else 1)\n"
+    )
+    env = dict(os.environ, RBM_NCCL_LIB="/nonexistent/libnccl-not-here.so.2")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr

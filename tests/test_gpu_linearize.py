@@ -183,3 +183,33 @@ def test_closed_loop_tracking_with_lqr():
     assert np.isfinite(err_fb).all()
     assert err_fb.max() < 0.05, err_fb.max()          # pulled back onto the plan (what remains is the integrator's O(dt) lag)
     assert np.median(err_open) > 5 * np.median(err_fb)  # without feedback the initial offsets persist / grow
+
+
+def test_generic_path_with_a_moving_base():
+    """with twist_0 != 0 the velocity block of A contains V_0 x (S qd) coupling terms; the generic evaluator used to
+    switch the base twist off for the velocity columns.  Checked against the literal transition FD on the same plant."""
+    g = load_golden("ref_inverse_hammer.npz")
+    from rigid_body_manipulation_b200.engine import Model
+
+    tw0 = np.array([0.3, -0.2, 0.1, 0.4, -0.5, 0.6])
+    m = Model(g["hposes_Rt"], g["simats"], g["uscrews"], tw0, g["dtwist_0"], pose_sen_llj=g["pose_sen_llj"])
+    assert m.kernel_path == "generic"
+    c = consts_of(g)
+    c["twist_0"] = tw0
+    n = 24
+    tr = sample_states(np.random.default_rng(11), n)
+    q, qd = tr[:, 0], tr[:, 1]
+    u = np.random.default_rng(12).standard_normal((n, 6)) * np.array([100, 100, 400, 1, 1, 1.0])
+    A, B, qdd = run(m, q, qd, u, dt=0.002, eps=1e-5, centered=True)
+    Ar, Br = lo.transition_fd(c, q, qd, u, dt=0.002, eps=1e-5, centered=True)
+    assert np.abs(qdd - lo.forward_dynamics(c, q, qd, u)).max() < 1e-9 * np.abs(qdd).max()
+    assert np.abs(A - Ar).max() < 2e-8
+    assert np.abs(B - Br).max() < 2e-8
+    # the coupling is really there: with the base twist switched off the velocity block differs by far more than the tolerance
+    c0 = dict(c, twist_0=np.zeros(6))
+    A0, _ = lo.transition_fd(c0, q, qd, u, dt=0.002, eps=1e-5, centered=True)
+    assert np.abs(A0[:, 6:, 6:] - Ar[:, 6:, 6:]).max() > 1e-5
+    # forward differences use the same (full-base) reference evaluation
+    A, B, _ = run(m, q, qd, u, dt=0.002, eps=1e-6, centered=False)
+    Ar, Br = lo.transition_fd(c, q, qd, u, dt=0.002, eps=1e-6, centered=False)
+    assert np.abs(A - Ar).max() < 1e-4

@@ -99,3 +99,24 @@ def test_fused_regressor_gram_matches_the_materialised_normal_equations(force_ge
     got = host_harness.regressor_gram(an, q, qd, qdd, f)
     assert got[111] == n
     assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
+
+
+def test_generic_linearisation_keeps_the_base_twist_in_the_velocity_columns():
+    """ADVICE r1 (csrc/rbm_dynamics.cuh GenericEval::id_velocity): a model with twist_0 != 0 has V_0 x (S qd) coupling terms in
+    d tau / d qd.  Host build of the same header, against the literal transition FD with the same moving base."""
+    c = pm.load_packaged("sequential", "hammer")
+    tw0 = np.array([0.3, -0.2, 0.1, 0.4, -0.5, 0.6])
+    an = engine.analyze_model(c.hposes_Rt, c.simats, c.uscrews, tw0, c.dtwist_0, pose_sen_llj=c.pose_sen_Rt)
+    assert an[0] == "generic"  # a moving base leaves the structure-specialised path
+    consts = dict(_consts(c), twist_0=tw0)
+    rng = np.random.default_rng(11)
+    n = 8
+    q, qd = _states(rng, n)
+    u = rng.standard_normal((n, 6)) * [100, 100, 400, 1, 1, 1.0]
+    for centered, eps, tol in ((True, 1e-5, 2e-8), (False, 1e-6, 1e-4)):
+        A, B, _ = host_harness.linearize(an, q, qd, u, dt=0.002, eps=eps, centered=centered)
+        Ar, Br = lo.transition_fd(consts, q, qd, u, dt=0.002, eps=eps, centered=centered)
+        assert np.abs(A - Ar).max() < tol and np.abs(B - Br).max() < 2e-7
+    A0, _ = lo.transition_fd(dict(consts, twist_0=np.zeros(6)), q, qd, u, dt=0.002, eps=1e-5, centered=True)
+    Ar, _ = lo.transition_fd(consts, q, qd, u, dt=0.002, eps=1e-5, centered=True)
+    assert np.abs(A0 - Ar).max() > 1e-5  # the coupling the old code dropped is far above the tolerance
