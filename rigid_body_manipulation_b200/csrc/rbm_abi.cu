@@ -196,6 +196,16 @@ int rnea_host(const rbm_model* m, const T* traj_host, T* tau_host, int64_t n, in
   return drain_pipe(m, rc, "rbm_rnea_host (synchronize)");
 }
 
+// Chunk of the SoA / planner-driven pipelines: a quarter of the batch, between 2^16 and 2^19 samples (measured on B200 + PCIe Gen5,
+// tools/bench_e2e_chunk.py -> profiles/r2_e2e_chunk.jsonl: four to sixteen chunks keep fill / drain short while every strided copy
+// still moves >= 0.5 MB per row).
+static int64_t default_chunk(int64_t n) {
+  int64_t c = n / 4;
+  if (c < (int64_t)1 << 16) c = (int64_t)1 << 16;
+  if (c > (int64_t)1 << 19) c = (int64_t)1 << 19;
+  return c;
+}
+
 // which rows of (q, qd, qdd) the inverse-dynamics kernel of this model reads: [3][nj], 1 = live
 static void live_inputs(const rbm_model* m, int32_t* mask) {
   for (int i = 0; i < 3 * m->nj; ++i) mask[i] = 1;
@@ -213,7 +223,7 @@ int rnea_host_soa(const rbm_model* m, const T* q_host, const T* qd_host, const T
   if (!q_host || !qd_host || !qdd_host || !tau_host) return invalid("rbm_rnea_host_soa: NULL buffer");
   if (ld < n) return invalid("rbm_rnea_host_soa: ld < n");
   const int nj = m->nj;
-  if (chunk <= 0) chunk = 1 << 17;
+  if (chunk <= 0) chunk = default_chunk(n);
   if (chunk > n) chunk = n;
   chunk = (chunk + 1) & ~int64_t(1);  // even device pitch: keeps the fp32 two-samples-per-thread kernel eligible
   DeviceGuard guard(m->device);
@@ -263,7 +273,7 @@ int rnea_planned_host(const rbm_model* m, const double* coeffs, const double* di
   if (ld < n) return invalid("rbm_rnea_planned_host: ld < n");
   if (!(timestep > 0.0)) return invalid("rbm_rnea_planned_host: timestep must be positive");
   const int nj = m->nj;
-  if (chunk <= 0) chunk = 1 << 17;
+  if (chunk <= 0) chunk = default_chunk(n);
   if (chunk > n) chunk = n;
   DeviceGuard guard(m->device);
   RBM_CUDA_TRY(guard.status());

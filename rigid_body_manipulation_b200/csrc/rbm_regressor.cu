@@ -438,7 +438,7 @@ __device__ __forceinline__ const T* live_stream(int k, const T* q, const T* qd, 
   return k < 3 ? q + (int64_t)(3 + k) * ld : k < 9 ? qd + (int64_t)(k - 3) * ld : k < 15 ? qdd + (int64_t)(k - 9) * ld : f + (int64_t)(k - 15) * ld;
 }
 
-template <class T, int PATH, bool SEN_DIAG>
+template <class T, int PATH, bool SEN_DIAG, bool PIPELINE>
 __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regressor_gram_pipe(const __grid_constant__ FastParams<T> P, const T* __restrict__ q,
                                                                                              const T* __restrict__ qd, const T* __restrict__ qdd,
                                                                                              const T* __restrict__ f, double* __restrict__ partials,
@@ -460,21 +460,23 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
   }
   __syncthreads();
 
-  // The issue cost of a bulk copy is paid by the issuing warp: lane 0 of warp w brings streams w, w + 8, w + 16 (< 21).
-  const int my_copies = (warp + 16 < kLiveStreams) ? 3 : 2;
+  // The issue cost of a bulk copy is paid by the issuing warp: lane 0 of warp w brings streams w, w + 8, w + 16 (< 21).  Their
+  // source rows are fixed for the whole kernel, so the pointers are formed once.
+  const int my_copies = (warp + 2 * NW < kLiveStreams) ? 3 : 2;
+  const T* my_src[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) my_src[i] = live_stream(warp + NW * i < kLiveStreams ? warp + NW * i : warp, q, qd, qdd, f, ld);
   auto issue = [&](int64_t it) {
     const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
     if (tile >= nfull) return;
     const int st = (int)(it % S);
     uint64_t* bar = &full[st];
     mbar_arrive_expect_tx(bar, my_copies * kRowBytes);
-    T* dst = buf + (size_t)st * kLiveStreams * kGramBlock;
+    T* dst = buf + ((size_t)st * kLiveStreams + warp) * kGramBlock;
     const int64_t s0 = tile * kGramBlock;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int k = warp + NW * i;
-      if (k < kLiveStreams) bulk_copy_g2s(dst + k * kGramBlock, live_stream(k, q, qd, qdd, f, ld) + s0, kRowBytes, bar);
-    }
+    bulk_copy_g2s(dst, my_src[0] + s0, kRowBytes, bar);
+    bulk_copy_g2s(dst + NW * kGramBlock, my_src[1] + s0, kRowBytes, bar);
+    if (my_copies == 3) bulk_copy_g2s(dst + 2 * NW * kGramBlock, my_src[2] + s0, kRowBytes, bar);
   };
   if (lane == 0) {
     for (int it = 0; it < S; ++it) issue(it);
@@ -483,10 +485,10 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
   T acc[kAcc];
 #pragma unroll
   for (int k = 0; k < kAcc; ++k) acc[k] = T(0);
-  GramCarry<T> z;  // the previous sample, not yet accumulated (zeros: accumulating them adds exact zeros)
+  GramCarry<T> z;  // PIPELINE: the previous sample, not yet accumulated (zeros: accumulating them adds exact zeros)
 #pragma unroll
   for (int k = 0; k < 3; ++k) { z.x[k] = T(0); z.w[k] = T(0); z.l[k] = T(0); z.f[k] = T(0); z.f[3 + k] = T(0); }
-  int since_flush = -1;  // the first accumulation is the all-zero carry and does not count
+  int since_flush = PIPELINE ? -1 : 0;  // PIPELINE: the first accumulation is the all-zero carry and does not count
   for (int64_t it = 0;; ++it) {
     const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
     if (tile >= nfull) break;
@@ -506,8 +508,15 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
     }
     __syncthreads();               // every thread holds its sample in registers: the stage can be refilled
     if (lane == 0) issue(it + S);  // each warp re-issues its streams
-    gram_step<T, PATH, SEN_DIAG>(P, rq, rqd, rqdd, zn, z, acc);
-    z = zn;
+    if constexpr (PIPELINE) {
+      gram_step<T, PATH, SEN_DIAG>(P, rq, rqd, rqdd, zn, z, acc);
+      z = zn;
+    } else {
+      T c[6], s[6];
+      fast_sincos<T, SeqIso>(rq, c, s);
+      gram_kinematics_cs<T, PATH, SEN_DIAG>(P, rq, c, s, rqd, rqdd, zn);
+      gram_accumulate_carry(acc, zn);
+    }
     if constexpr (sizeof(T) == 4) {
       if (++since_flush == kFlush) {
         since_flush = 0;
@@ -515,12 +524,12 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
       }
     }
   }
-  gram_accumulate_carry(acc, z);
+  if constexpr (PIPELINE) gram_accumulate_carry(acc, z);
   // ragged tail (n % 256 samples): owned by the CTA that would have received tile `nfull`
   if ((nfull % gridDim.x) == blockIdx.x) {
     const int64_t s = nfull * kGramBlock + tid;
     if (s < n) {
-      T rq[6], rqd[6], rqdd[6];
+      T rq[6], rqd[6], rqdd[6], c[6], sn[6];
       rq[0] = rq[1] = rq[2] = T(0);
 #pragma unroll
       for (int k = 0; k < 3; ++k) rq[3 + k] = __ldg(q + (3 + k) * ld + s);
@@ -530,14 +539,184 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
         rqdd[k] = __ldg(qdd + k * ld + s);
         z.f[k] = __ldg(f + k * ld + s);
       }
-      GramCarry<T> none = z;  // accumulated right below, in the same step as its own kinematics would be for the NEXT sample
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { none.x[k] = T(0); none.w[k] = T(0); none.l[k] = T(0); none.f[k] = T(0); none.f[3 + k] = T(0); }
-      gram_step<T, PATH, SEN_DIAG>(P, rq, rqd, rqdd, z, none, acc);
+      fast_sincos<T, SeqIso>(rq, c, sn);
+      gram_kinematics_cs<T, PATH, SEN_DIAG>(P, rq, c, sn, rqd, rqdd, z);
       gram_accumulate_carry(acc, z);
     }
   }
   gram_block_epilogue<T>(acc, red, partials);
+}
+
+// ---- warp-pair variant: 12 warps per SM instead of 8 by halving the accumulators each thread keeps ---------------------------------
+// Round-2 ncu reading of the kernels above (fp64): the accumulation phase is FP64-pipe bound, the kinematic chain phase is
+// LATENCY bound (two warps per scheduler issue ~46 % of the cycles), and the warp count is pinned by the 70 double accumulators
+// (140 registers) every thread keeps.  Here warps work in pairs on the SAME 64 samples: each warp runs the kinematics of its own
+// 32 samples, publishes (x, w, dw) -- 9 scalars per sample -- in shared memory, and after a 64-thread named barrier accumulates
+// ONE HALF of the 70 entries (gram_accumulate_set<0 / 1>, rbm_gram.cuh) for both its own and its partner's samples.  36
+// accumulators per thread -> <= 168 registers -> 384 threads per SM.  The input stage is released one iteration late (the wrench
+// rows of the partner's samples are read from it), so nothing has to be parked in registers across the CTA barrier.
+constexpr int kPairWarps = 12;
+constexpr int kPairBlock = kPairWarps * 32;
+constexpr int kPairStages = 3;
+constexpr int kPairZ = 9;  // x(3) w(3) dw(3)
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <class T, int N>
+__device__ __forceinline__ void gram_flush_f32_n(float (&acc)[N], double* red_warp, int lane) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == (k & 31)) red_warp[k] += (double)v;
+    acc[k] = 0.f;
+  }
+}
+
+template <int SET, class T>
+__device__ __forceinline__ void pair_accumulate(T (&acc)[kSetMax], const T (&x)[3], const T (&w)[3], const T (&l)[3], const T (&fs)[6]) {
+  T top[3][4], bot[3][9];
+  regressor_blocks_xwl(x, w, l, top, bot);
+  gram_accumulate_set<SET>(acc, top, bot, fs);
+}
+
+template <class T, int PATH, bool SEN_DIAG>
+__global__ void __launch_bounds__(kPairBlock, 1) k_regressor_gram_pair(const __grid_constant__ FastParams<T> P, const T* __restrict__ q,
+                                                                       const T* __restrict__ qd, const T* __restrict__ qdd, const T* __restrict__ f,
+                                                                       double* __restrict__ partials, int64_t n, int64_t ld) {
+  constexpr int S = kPairStages, NW = kPairWarps, TILE = kPairBlock, HALF = NW / 2;
+  constexpr uint32_t kRowBytes = TILE * sizeof(T);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* buf = reinterpret_cast<T*>(smem_raw);                   // [S][kLiveStreams][TILE]
+  T* zbuf = buf + (size_t)S * kLiveStreams * TILE;           // [NW][kPairZ][32]
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ double red[NW][kSetMax];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int set = warp < HALF ? 0 : 1;
+  const int partner = warp < HALF ? warp + HALF : warp - HALF;
+  const int pair_bar = 1 + (warp < HALF ? warp : warp - HALF);  // named barriers 1..6 (0 is __syncthreads)
+  const int64_t nfull = n / TILE;
+  for (int k = lane; k < kSetMax; k += 32) red[warp][k] = 0.0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], NW);
+    mbar_init_fence();
+  }
+  __syncthreads();
+
+  // 21 copies per tile over 12 warps: warp w brings streams w and (w + 12 < 21) w + 12
+  const int my_copies = (warp + NW < kLiveStreams) ? 2 : 1;
+  const T* my_src[2];
+  my_src[0] = live_stream(warp, q, qd, qdd, f, ld);
+  my_src[1] = live_stream(warp + NW < kLiveStreams ? warp + NW : warp, q, qd, qdd, f, ld);
+  auto issue = [&](int64_t it) {
+    const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= nfull) return;
+    const int st = (int)(it % S);
+    uint64_t* bar = &full[st];
+    mbar_arrive_expect_tx(bar, my_copies * kRowBytes);
+    T* dst = buf + ((size_t)st * kLiveStreams + warp) * TILE;
+    const int64_t s0 = tile * TILE;
+    bulk_copy_g2s(dst, my_src[0] + s0, kRowBytes, bar);
+    if (my_copies == 2) bulk_copy_g2s(dst + NW * TILE, my_src[1] + s0, kRowBytes, bar);
+  };
+  if (lane == 0) {
+    for (int it = 0; it < S; ++it) issue(it);
+  }
+
+  T acc[kSetMax];
+#pragma unroll
+  for (int k = 0; k < kSetMax; ++k) acc[k] = T(0);
+
+  // one tile: own kinematics -> exchange -> this warp's half of the entries for both samples of the lane pair
+  auto process = [&](const T* stage, bool valid) {
+    const T* src = stage + tid;
+    T rq[6], rqd[6], rqdd[6], c[6], sn[6];
+    rq[0] = rq[1] = rq[2] = T(0);  // dead inputs of the sequential structure
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rq[3 + k] = src[k * TILE];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      rqd[k] = src[(3 + k) * TILE];
+      rqdd[k] = src[(9 + k) * TILE];
+    }
+    GramCarry<T> z;
+    fast_sincos<T, SeqIso>(rq, c, sn);
+    gram_kinematics_cs<T, PATH, SEN_DIAG>(P, rq, c, sn, rqd, rqdd, z);
+    if (!valid) {  // padding sample of the ragged tail: contributes exact zeros (its wrench rows are zero too)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { z.x[k] = T(0); z.w[k] = T(0); z.l[k] = T(0); }
+    }
+    T* zb = zbuf + (size_t)warp * kPairZ * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { zb[k * 32] = z.x[k]; zb[(3 + k) * 32] = z.w[k]; zb[(6 + k) * 32] = z.l[k]; }
+    named_bar_sync(pair_bar, 64);
+    const T* zp = zbuf + (size_t)partner * kPairZ * 32 + lane;
+    T px[3], pw[3], pl[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { px[k] = zp[k * 32]; pw[k] = zp[(3 + k) * 32]; pl[k] = zp[(6 + k) * 32]; }
+    if (set == 0) {
+      T fo[6], fp[6];
+      const T* fsrc = stage + 15 * TILE;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { fo[k] = fsrc[k * TILE + tid]; fp[k] = fsrc[k * TILE + partner * 32 + lane]; }
+      pair_accumulate<0>(acc, z.x, z.w, z.l, fo);
+      pair_accumulate<0>(acc, px, pw, pl, fp);
+    } else {
+      const T none[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};  // set 1 holds no wrench entry
+      pair_accumulate<1>(acc, z.x, z.w, z.l, none);
+      pair_accumulate<1>(acc, px, pw, pl, none);
+    }
+  };
+
+  int since_flush = 0;
+  for (int64_t it = 0;; ++it) {
+    const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= nfull) break;
+    const int st = (int)(it % S);
+    mbar_wait(&full[st], (uint32_t)((it / S) & 1));
+    __syncthreads();  // every warp is done with iteration it - 1: its stage and the exchange buffers are free
+    if (lane == 0 && it > 0) issue(it - 1 + S);  // refill the stage consumed by the PREVIOUS iteration
+    process(buf + (size_t)st * kLiveStreams * TILE, true);
+    if constexpr (sizeof(T) == 4) {
+      if (++since_flush == kFlush / 2) {  // two samples per thread and iteration
+        since_flush = 0;
+        gram_flush_f32_n<T, kSetMax>(acc, red[warp], lane);
+      }
+    }
+  }
+  // ragged tail (n % 384 samples): staged by hand into stage 0 (zeros beyond n) by the CTA that would have received tile `nfull`
+  if ((nfull % gridDim.x) == blockIdx.x && nfull * TILE < n) {
+    __syncthreads();
+    const int64_t s = nfull * TILE + tid;
+    const bool valid = s < n;
+#pragma unroll
+    for (int k = 0; k < kLiveStreams; ++k) buf[(size_t)k * TILE + tid] = valid ? __ldg(live_stream(k, q, qd, qdd, f, ld) + s) : T(0);
+    __syncthreads();
+    process(buf, valid);
+  }
+  // epilogue: registers -> per-warp doubles -> fixed-order sum over the six warps of each set -> partials[blockIdx][70]
+  if constexpr (sizeof(T) == 4) {
+    gram_flush_f32_n<T, kSetMax>(acc, red[warp], lane);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kSetMax; ++k) {
+      double v = acc[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == (k & 31)) red[warp][k] += v;
+    }
+  }
+  __syncthreads();
+  if (tid < kAcc) {
+    int kset, local;
+    pair_locate(tid, kset, local);
+    double v = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < HALF; ++wq) v += red[kset * HALF + wq][local];  // fixed order
+    partials[(int64_t)blockIdx.x * kAcc + tid] = v;
+  }
 }
 
 // partials [nblocks][70] -> pack [112] = [Y^T Y (100, row-major) | Y^T f (10) | f^T f | n]
@@ -667,11 +846,12 @@ int launch_regressor_gram_grouped(const rbm_model* m, const T* q, const T* qd, c
 template int launch_regressor_gram_grouped<double>(const rbm_model*, const double*, const double*, const double*, const double*, int64_t, int64_t, int64_t, double*,
                                                    int64_t, int64_t, int64_t, cudaStream_t);
 
-// development knob: RBM_GRAM_VARIANT=0 selects the round-1 TMA kernel (24 streams, no software pipelining) for A/B timing
+// development knob for A/B timing of the TMA-fed Gram kernels: RBM_GRAM_VARIANT = 0 round-1 kernel (24 streams) | 1 live streams +
+// software-pipelined accumulation | 2 live streams (default) | 3 warp-pair split
 static int gram_variant() {
   static const int v = [] {
     const char* e = getenv("RBM_GRAM_VARIANT");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 2;
   }();
   return v;
 }
@@ -688,11 +868,26 @@ int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* 
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const bool tma_ok = m->path != PATH_GENERIC && al16(q) && al16(qd) && al16(qdd) && al16(f) && ((ld * sizeof(T)) % 16 == 0) && n >= kGramBlock &&
                         !m->no_tma;
-    if (tma_ok && gram_variant() == 0) {  // round-1 kernel, kept for A/B runs (RBM_GRAM_VARIANT=0)
+    const int variant = gram_variant();
+    const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
+    const bool diag = P.sen_diag != T(0);
+    // picks the instantiation for (kernel path, sensor-pose form), raises its dynamic shared-memory limit once per device, launches
+#define RBM_LAUNCH_GRAM(KERNEL, BLOCK, SMEM, ...)                                                                                  \
+  do {                                                                                                                             \
+    auto kfn = m->path == PATH_SEQ_ISO ? (diag ? KERNEL<T, PATH_SEQ_ISO, true __VA_ARGS__> : KERNEL<T, PATH_SEQ_ISO, false __VA_ARGS__>)       \
+                                       : (diag ? KERNEL<T, PATH_SEQ_RIGID, true __VA_ARGS__> : KERNEL<T, PATH_SEQ_RIGID, false __VA_ARGS__>);  \
+    static std::atomic<const void*> ready[64][4];                                                                                  \
+    const int slot = (m->path == PATH_SEQ_ISO ? 0 : 2) + (diag ? 0 : 1);                                                           \
+    if (ready[dev][slot].load(std::memory_order_acquire) != (const void*)kfn) {                                                    \
+      RBM_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));                           \
+      ready[dev][slot].store((const void*)kfn, std::memory_order_release);                                                         \
+    }                                                                                                                              \
+    kfn<<<grid, BLOCK, SMEM, st>>>(P, q, qd, qdd, f, partials, n, ld);                                                              \
+  } while (0)
+    if (tma_ok && variant == 0) {  // round-1 kernel, kept for A/B runs (RBM_GRAM_VARIANT=0)
       grid = gram_grid(m, n, sizeof(T) == 4 ? 2 : 1);  // fp32: 119 registers, 96 KB of stages: two CTAs per SM
       constexpr size_t smem = (size_t)kGramStages * kStreams * kGramBlock * sizeof(T);
       static std::atomic<bool> attr_set[64];  // function attributes are per device
-      const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
       if (!attr_set[dev].load(std::memory_order_acquire)) {
         RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_tma<T, PATH_SEQ_ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_tma<T, PATH_SEQ_RIGID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -700,26 +895,18 @@ int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* 
       }
       if (m->path == PATH_SEQ_ISO) k_regressor_gram_tma<T, PATH_SEQ_ISO><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
       else k_regressor_gram_tma<T, PATH_SEQ_RIGID><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
+    } else if (tma_ok && variant == 3 && n >= kPairBlock) {  // warp-pair split: 12 warps per SM
+      const int64_t tiles = n / kPairBlock;
+      const int64_t cap = sm_count(m->device);
+      grid = (int)(tiles < cap ? tiles : cap);
+      constexpr size_t smem = ((size_t)kPairStages * kLiveStreams * kPairBlock + (size_t)kPairWarps * kPairZ * 32) * sizeof(T);
+      RBM_LAUNCH_GRAM(k_regressor_gram_pair, kPairBlock, smem, );
     } else if (tma_ok) {
       grid = gram_grid(m, n, sizeof(T) == 4 ? 2 : 1);  // fp32: two CTAs per SM (105 KB of stages each)
       constexpr size_t smem = (size_t)kPipeStages * kLiveStreams * kGramBlock * sizeof(T);
-      static std::atomic<bool> attr_set[64];
-      const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
-      if (!attr_set[dev].load(std::memory_order_acquire)) {
-        RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_pipe<T, PATH_SEQ_ISO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_pipe<T, PATH_SEQ_RIGID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_pipe<T, PATH_SEQ_ISO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RBM_CUDA_TRY(cudaFuncSetAttribute(k_regressor_gram_pipe<T, PATH_SEQ_RIGID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[dev].store(true, std::memory_order_release);
-      }
-      const bool diag = P.sen_diag != T(0);
-      if (m->path == PATH_SEQ_ISO) {
-        if (diag) k_regressor_gram_pipe<T, PATH_SEQ_ISO, true><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
-        else k_regressor_gram_pipe<T, PATH_SEQ_ISO, false><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
-      } else {
-        if (diag) k_regressor_gram_pipe<T, PATH_SEQ_RIGID, true><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
-        else k_regressor_gram_pipe<T, PATH_SEQ_RIGID, false><<<grid, kGramBlock, smem, st>>>(P, q, qd, qdd, f, partials, n, ld);
-      }
+      if (variant == 1) RBM_LAUNCH_GRAM(k_regressor_gram_pipe, kGramBlock, smem, , true);
+      else RBM_LAUNCH_GRAM(k_regressor_gram_pipe, kGramBlock, smem, , false);
+#undef RBM_LAUNCH_GRAM
     } else if (m->path == PATH_SEQ_ISO) {
       k_regressor_gram<T, PATH_SEQ_ISO><<<grid, kGramBlock, 0, st>>>(P, gp, m->nj, np, q, qd, qdd, f, partials, n, ld);
     } else if (m->path == PATH_SEQ_RIGID) {

@@ -33,15 +33,25 @@ def check_common(d):
 
 
 def test_default_workload_line():
-    d = run_bench("--steps", "5", "--warmup", "3", "--samples", "262144", "--cpu-samples", "256")
+    d = run_bench("--steps", "5", "--warmup", "3", "--samples", "262144", "--cpu-samples", "256", "--gram-samples", "300000")
     check_common(d)
     assert d["metric"] == "rnea_samples_per_s" and d["unit"] == "samples/s" and d["dtype"] == "f64" and d["n_gpus"] == 1
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert r["algorithmic_bytes_per_launch"] == 192 * 262144
     assert d["gpu_launches"] == 5
-    assert d["e2e"]["h2d_bytes_per_step"] == 144 * 262144 and d["e2e"]["d2h_bytes_per_step"] == 48 * 262144
+    # headline e2e = the SoA host entry: only the 15 live rows are uploaded (the kernel never reads the three gantry positions)
+    assert r["live_input_rows"] == 15 and r["bytes_moved_per_launch"] == 168 * 262144 and abs(r["frac_moved"] - r["frac"] * 168 / 192) < 1e-12
+    assert d["e2e"]["h2d_bytes_per_step"] == 120 * 262144 and d["e2e"]["d2h_bytes_per_step"] == 48 * 262144
     assert d["e2e"]["value"] < d["value"]  # host copies are inside the e2e timed region
+    v = d["e2e"]["variants"]
+    assert v["aos_host"]["h2d_bytes_per_step"] == 144 * 262144 and v["planned_host"]["h2d_bytes_per_step"] == 0 and v["planned_host"]["value"] > 0
+    # the other BASELINE configs ride on the same line
+    x = d["extra"]
+    for dt_ in ("f64", "f32"):
+        gx = x["gram"][dt_]
+        assert gx["samples_per_gpu"] == 300_000 and gx["value"] > 0 and gx["pack_n_ok"] is True and 0 < gx["frac"] < 2
+    assert x["linearize"]["value"] > 0 and x["rnea_f32"]["value"] > 0
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
     k = d["clocks"]
@@ -52,7 +62,7 @@ def test_default_workload_line():
 @pytest.mark.parametrize("extra", [("--dtype", "f32"), ("--workload", "gram", "--samples", "262144"), ("--workload", "gram", "--dtype", "f32", "--samples", "262144"),
                                    ("--workload", "linearize", "--samples", "65536")])
 def test_other_workloads(extra):
-    d = run_bench("--steps", "3", "--warmup", "3", "--no-cpu", *extra)
+    d = run_bench("--steps", "3", "--warmup", "3", "--no-cpu", "--no-extra", *extra)
     check_common(d)
     assert 0 < d["roofline"]["frac"] < 2
 
