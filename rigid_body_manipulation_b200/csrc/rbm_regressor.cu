@@ -884,6 +884,16 @@ int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* 
     }                                                                                                                              \
     kfn<<<grid, BLOCK, SMEM, st>>>(P, q, qd, qdd, f, partials, n, ld);                                                              \
   } while (0)
+    if constexpr (sizeof(T) == 4) {
+      if (tma_ok && (variant == 4 || m->gram_tc)) {  // fp32 mode on the tensor cores (rbm_gram_tc.cu), opt-in
+        grid = tc_gram_grid(sm_count(m->device), n);
+        int rc = launch_regressor_gram_tc(m, q, qd, qdd, f, partials, n, ld, grid, st);
+        if (rc != RBM_OK) return rc;
+        k_gram_finalize<<<1, 128, 0, st>>>(partials, grid, (double)n, pack);
+        RBM_CUDA_TRY(cudaGetLastError());
+        return RBM_OK;
+      }
+    }
     if (tma_ok && variant == 0) {  // round-1 kernel, kept for A/B runs (RBM_GRAM_VARIANT=0)
       grid = gram_grid(m, n, sizeof(T) == 4 ? 2 : 1);  // fp32: 119 registers, 96 KB of stages: two CTAs per SM
       constexpr size_t smem = (size_t)kGramStages * kStreams * kGramBlock * sizeof(T);
