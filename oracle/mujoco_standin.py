@@ -59,6 +59,10 @@ class StandinModel:
         self.G_sensed = ro.sensor_inertia(c.simat_sen_obj, self.pose_sen_Rt)
         self.model_constants = c
 
+    def forward_kinematics(self, d):
+        """look-alike protocol of rigid_body_manipulation_b200.mujoco_bridge.refresh_kinematics (what mujoco.mj_forward does for a real model)"""
+        mj_forward(self, d)
+
     @property
     def opt(self):
         class _Opt:

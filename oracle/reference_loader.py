@@ -104,3 +104,50 @@ def load_simulation() -> ReferenceModules:
         sys.path[:] = saved_path
     _sim_cache = ns
     return ns
+
+
+_dropin_sim_cache = None
+
+
+def load_simulation_on_dropin(dropin_root: str) -> ReferenceModules:
+    """The reference's `core/simulate.py`, unmodified, importing the DROP-IN packages instead of its own: `dropin_root` (the product's
+    rigid_body_manipulation_b200/dropin directory: `dynamics`, `transformations`, `controllers`, `planners`) precedes the reference
+    checkout on sys.path, so `import dynamics as dyn`, `from transformations import Poses` (core/simulate.py:13-15) and the controller /
+    planner modules resolve to the replacement, while `sensors`, `utilities`, `visualization` still come from the reference and
+    `liegroups` / `mujoco` / `matplotlib` from the shims.  Returns `.simulate`, `.dynamics`, `.transformations`, `.controllers`,
+    `.planner` (module objects), each asserted to come from where it should."""
+    global _dropin_sim_cache
+    if _dropin_sim_cache is not None:
+        return _dropin_sim_cache
+    if not available():
+        raise FileNotFoundError(f"reference checkout not found at {REFERENCE_ROOT}")
+    import importlib.util
+
+    saved_path = list(sys.path)
+    saved_mods = {k: v for k, v in sys.modules.items() if k.split(".")[0] in _SHADOWED}
+    for k in saved_mods:
+        del sys.modules[k]
+    try:
+        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.insert(0, _SHIMS)
+        sys.path.insert(0, dropin_root)
+        ns = ReferenceModules()
+        ns.dynamics = importlib.import_module("dynamics")
+        ns.transformations = importlib.import_module("transformations")
+        ns.planner = importlib.import_module("planners.joint_position_planner")
+        ns.controllers = importlib.import_module("controllers")
+        spec = importlib.util.spec_from_file_location("_rbm_ref_simulate", os.path.join(REFERENCE_ROOT, "core", "simulate.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ns.simulate = mod
+        real = os.path.realpath
+        for m_ in (ns.dynamics, ns.transformations, ns.planner, ns.controllers):
+            assert real(m_.__file__).startswith(real(dropin_root)), m_.__file__
+        assert mod.dyn is ns.dynamics and real(sys.modules["sensors"].__file__).startswith(real(REFERENCE_ROOT))
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in _SHADOWED]:
+            del sys.modules[k]
+        sys.modules.update(saved_mods)
+        sys.path[:] = saved_path
+    _dropin_sim_cache = ns
+    return ns

@@ -61,7 +61,7 @@ def _pose_key(p):
 def _cached_model(hposes_body_parent, simats_body, uscrews_body, twist_0, dtwist_0, wrench_tip, pose_tip_ee):
     """Content-keyed lookup (a few microseconds of hashing per call; the arrays are mutable, so identity is not enough)."""
     nj = len(uscrews_body)
-    key = (torch.cuda.current_device(), np.asarray(uscrews_body, dtype=np.float64).tobytes(), np.asarray(simats_body, dtype=np.float64).tobytes(),
+    key = (_engine.current_device(), np.asarray(uscrews_body, dtype=np.float64).tobytes(), np.asarray(simats_body, dtype=np.float64).tobytes(),
            np.asarray(twist_0, dtype=np.float64).tobytes(), np.asarray(dtwist_0, dtype=np.float64).tobytes(),
            np.asarray(wrench_tip, dtype=np.float64).tobytes(), _pose_key(pose_tip_ee)) + tuple(_pose_key(h) for h in hposes_body_parent[: nj + 1])
     m = _MODELS.get(key)

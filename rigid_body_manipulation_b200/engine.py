@@ -41,6 +41,11 @@ def poses_to_Rt(poses) -> np.ndarray:
     return np.stack([pose_to_Rt(p) for p in poses])
 
 
+def current_device() -> int:
+    """Index of the CUDA device new models are created on."""
+    return torch.cuda.current_device()
+
+
 def _ptr(a):
     if a is None:
         return None

@@ -15,9 +15,15 @@ SLIDE, HINGE = 2, 3  # mjtJoint
 
 
 def refresh_kinematics(m, d) -> bool:
-    """For real MuJoCo objects: run mj_forward so that d.xpos / xmat / xipos / site_x* describe the current qpos.  The reference
-    relies on mjd_transitionFD (inside the LQR constructor, controllers/lqr.py:34-36) for this side effect before simulate()
-    reads the world poses; the replacement StateSpace must therefore provide it.  Returns False for look-alike objects."""
+    """Run the forward kinematics so that d.xpos / xmat / xipos / site_x* describe the current qpos.  The reference relies on
+    mjd_transitionFD (inside the LQR constructor, controllers/lqr.py:34-36) for this side effect before simulate() reads the world
+    poses; the replacement StateSpace must therefore provide it.  Real MuJoCo objects get mujoco.mj_forward; MuJoCo-free look-alike
+    models may offer the same service as a `forward_kinematics(d)` method.  Returns False when neither applies (the caller's arrays
+    are then taken as they are)."""
+    fk = getattr(m, "forward_kinematics", None)
+    if callable(fk):
+        fk(d)
+        return True
     try:
         import mujoco
     except ImportError:

@@ -22,7 +22,7 @@ def nvcc_path():
 
 def build():
     os.makedirs(OUT, exist_ok=True)
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rbm_rnea.cuh", "rbm_typed.cuh", "rbm_trig.cuh", "rbm_model.cuh", "rbm_dynamics.cuh", "rbm_gram.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rbm_rnea.cuh", "rbm_typed.cuh", "rbm_trig.cuh", "rbm_model.cuh", "rbm_dynamics.cuh", "rbm_gram.cuh", "rbm_setup.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     nvcc = nvcc_path()
@@ -157,3 +157,55 @@ def regressor_gram(analysis, q, qd, qdd, f):
     rc = lib().h_regressor_gram_f64(path, _p(fp), _p(gp), nj, *[_p(a) for a in arrs], _p(pack), C.c_int64(n))
     assert rc == 0
     return pack
+
+
+# ---- csrc/rbm_setup.cuh on the host (the batched frame-algebra helpers) ------------------------------------------------------------
+def _c64(a, shape_tail):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    assert tuple(a.shape[1:]) == tuple(shape_tail), (a.shape, shape_tail)
+    return a
+
+
+def transfer_simat(poses_Rt, simats, adjoint_form=False):
+    P, G = _c64(poses_Rt, (12,)), _c64(simats, (6, 6))
+    out = np.empty_like(G)
+    assert lib().h_transfer_simat_f64(_p(P), _p(G), _p(out), C.c_int64(len(P)), C.c_int(1 if adjoint_form else 0)) == 0
+    return out
+
+
+def coordinate_transfer_imat(poses_Rt, imats, mass):
+    P, I, m = _c64(poses_Rt, (12,)), _c64(imats, (3, 3)), _c64(np.atleast_1d(mass), ())
+    out = np.empty_like(I)
+    assert lib().h_transfer_imat_f64(_p(P), _p(I), _p(m), _p(out), C.c_int64(len(P))) == 0
+    return out
+
+
+def spatial_inertia(mass, diag):
+    m, d = _c64(np.atleast_1d(mass), ()), _c64(diag, (3,))
+    out = np.empty((len(m), 6, 6))
+    assert lib().h_spatial_inertia_f64(_p(m), _p(d), _p(out), C.c_int64(len(m))) == 0
+    return out
+
+
+def compose_poses(trans, rot):
+    rot = np.ascontiguousarray(rot, dtype=np.float64)
+    t = _c64(trans, (3,))
+    out, status = np.empty((len(t), 12)), np.empty(len(t), dtype=np.int32)
+    assert lib().h_compose_f64(_p(t), _p(rot), C.c_int(rot.shape[1]), _p(out), _p(status), C.c_int64(len(t))) == 0
+    return out, status
+
+
+def point_motion(twists, dtwists, points, want_acc=True):
+    tw, p = _c64(twists, (6,)), _c64(points, (3,))
+    dtw = _c64(dtwists, (6,)) if (want_acc and dtwists is not None) else None
+    lv = np.empty_like(p)
+    la = np.empty_like(p) if dtw is not None else None
+    assert lib().h_point_motion_f64(_p(tw), _p(dtw), _p(p), _p(lv), _p(la), C.c_int64(len(p))) == 0
+    return lv, la
+
+
+def regressor_rows(twists, dtwists):
+    tw, dtw = _c64(twists, (6,)), _c64(dtwists, (6,))
+    Y = np.empty((len(tw), 6, 10))
+    assert lib().h_regressor_rows_f64(_p(tw), _p(dtw), _p(Y), C.c_int64(len(tw))) == 0
+    return Y

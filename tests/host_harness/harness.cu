@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY (never part of librbm_b200.so, never reachable from the package).
 //
 // The device arithmetic of the kernels lives in __host__ __device__ headers (csrc/rbm_typed.cuh, rbm_trig.cuh, rbm_rnea.cuh,
-// rbm_dynamics.cuh).
+// rbm_dynamics.cuh, rbm_setup.cuh).
 // This translation unit instantiates the SAME per-sample functions for the host and exposes them through a tiny C interface,
 // so that the `-m "not gpu"` suite can check the kernels' mathematics -- the structure-specialised typed recursion, the generic
 // recursion, the regressor blocks, the reduced (inertia-only / velocity-only) evaluations -- against the reference-generated
@@ -14,6 +14,7 @@
 #include "rbm_dynamics.cuh"
 #include "rbm_gram.cuh"
 #include "rbm_rnea.cuh"
+#include "rbm_setup.cuh"
 
 using namespace rbm;
 
@@ -197,3 +198,42 @@ extern "C" int h_regressor_gram_f64(int path, const double* fast_params, const d
   pack[111] = (double)n;
   return 0;
 }
+
+
+// ---- rbm_setup.cuh: the small frame-algebra helpers, one item per loop iteration (the kernels run one item per thread) ----------------
+extern "C" {
+int h_transfer_simat_f64(const double* poses, const double* simats, double* out, int64_t n, int mode) {
+  for (int64_t s = 0; s < n; ++s) transfer_simat_item(poses + 12 * s, simats + 36 * s, out + 36 * s, mode);
+  return 0;
+}
+int h_transfer_imat_f64(const double* poses, const double* imats, const double* mass, double* out, int64_t n) {
+  for (int64_t s = 0; s < n; ++s) transfer_imat_item(poses + 12 * s, imats + 9 * s, mass[s], out + 9 * s);
+  return 0;
+}
+int h_spatial_inertia_f64(const double* mass, const double* diag, double* out, int64_t n) {
+  for (int64_t s = 0; s < n; ++s) spatial_inertia_item(mass[s], diag + 3 * s, out + 36 * s);
+  return 0;
+}
+int h_compose_f64(const double* trans, const double* rot, int rot_len, double* out, int32_t* status, int64_t n) {
+  for (int64_t s = 0; s < n; ++s) status[s] = compose_item(trans + 3 * s, rot + (int64_t)rot_len * s, rot_len, out + 12 * s);
+  return 0;
+}
+int h_point_motion_f64(const double* tw, const double* dtw, const double* pts, double* linvel, double* linacc, int64_t n) {
+  for (int64_t s = 0; s < n; ++s)
+    point_motion_item(tw + 6 * s, dtw ? dtw + 6 * s : nullptr, pts + 3 * s, linvel ? linvel + 3 * s : nullptr, linacc ? linacc + 3 * s : nullptr);
+  return 0;
+}
+int h_regressor_rows_f64(const double* V, const double* dV, double* Y, int64_t n) {
+  for (int64_t s = 0; s < n; ++s) {
+    double top[3][4], bot[3][9];
+    regressor_blocks(V + 6 * s, dV + 6 * s, top, bot);
+    double* y = Y + 60 * s;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 10; ++c) {
+        y[r * 10 + c] = c < 4 ? top[r][c] : 0.0;
+        y[(3 + r) * 10 + c] = c == 0 ? 0.0 : bot[r][c - 1];
+      }
+  }
+  return 0;
+}
+}  // extern "C"

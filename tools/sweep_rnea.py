@@ -1,6 +1,10 @@
-"""BASELINE.json configs[4]: throughput sweep of the batched inverse dynamics over batch sizes, fp32 and fp64, on this rank's GPU.
+"""BASELINE.json configs[4]: throughput sweep of the batched inverse dynamics over batch sizes, fp32 and fp64, at 1/2/4/8 GPUs.
 
     python tools/sweep_rnea.py [--max-exp 9] [--out profiles/r1_sweep_rnea.jsonl]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/sweep_rnea.py --out profiles/r2_sweep_rnea_8gpu.jsonl
+
+Under torchrun the B samples of every size are sharded contiguously over the ranks (distributed.shard_range; no data-path collective),
+each launch loop is bracketed by barrier + synchronize, timed with CUDA events, and the MAX over ranks is reported by rank 0.
 
 Inputs are generated on the device (seeded); every size is timed over enough back-to-back launches to last >= ~50 ms,
 with rotating buffer sets when one batch is smaller than 3x the L2.  One JSON line per (dtype, B).  The planner-driven
@@ -32,19 +36,33 @@ def gen(B, dt, gen_):
     return q, qd, qdd
 
 
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+
+
+def barrier():
+    if WORLD > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
 def timed(fn, min_ms=50.0):
+    """ms per call; the repetition count is decided from the max-reduced time, so it is identical on every rank"""
     for _ in range(3):
         fn()
-    torch.cuda.synchronize()
     reps = 4
     while True:
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
             fn()
         e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if WORLD > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        ms = ms.item()
         if ms >= min_ms or reps >= 1 << 16:
             return ms / reps
         reps *= 4
@@ -56,21 +74,32 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--generic", action="store_true", help="force the generic (any-model) kernel")
     ap.add_argument("--min-exp", type=int, default=4)
+    ap.add_argument("--dtypes", default="f32,f64")
     args = ap.parse_args()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if WORLD > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from rigid_body_manipulation_b200 import distributed as rbm_dist
+
     c = rbm_model.load_packaged("sequential", "hammer")
-    m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, force_generic=args.generic)
+    m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, force_generic=args.generic, device=local)
     free_b = torch.cuda.mem_get_info()[0]
     lines = []
     for name, dt, es in (("f32", torch.float32, 4), ("f64", torch.float64, 8)):
+        if name not in args.dtypes.split(","):
+            continue
         for e in range(args.min_exp, args.max_exp + 1):
-            B = 10**e
+            B_total = 10**e
+            a_, b_ = rbm_dist.shard_range(B_total, RANK, WORLD)
+            B = max(b_ - a_, 2)  # this rank's shard (>= 2 keeps the degenerate sizes launchable on every rank)
             alg = 24 * es * B
             nset = 1 if alg > 8 * L2 else int(np.ceil(3 * L2 / alg)) + 1
             nset = min(nset, 64)
             if nset * alg > 0.9 * free_b:
                 lines.append({"dtype": name, "B": B, "skipped": f"{nset * alg / 1e9:.0f} GB does not fit in HBM on one GPU; chunk or shard"})
                 continue
-            g = torch.Generator(device="cuda").manual_seed(1234)
+            g = torch.Generator(device="cuda").manual_seed(1234 + RANK)
             sets = [gen(B, dt, g) + (torch.empty((6, B), dtype=dt, device="cuda"),) for _ in range(nset)]
             k = [0]
 
@@ -88,14 +117,16 @@ def main():
                 m.rnea_planned(plan, n=B, step0=0.0, stride=1500.0 / B, dtype=dt, tau=taus[k[0] % nset])
 
             pms = timed(pstep)
-            gbs = alg / (ms * 1e-3) / 1e9
-            lines.append({"kernel_path": m.kernel_path, "dtype": name, "B": B, "ms": ms, "samples_per_s": B / (ms * 1e-3), "GBps_algorithmic": gbs, "frac_of_measured_hbm": gbs / PEAK,
-                          "buffer_sets": nset, "planned_ms": pms, "planned_samples_per_s": B / (pms * 1e-3),
-                          "planned_GBps_algorithmic": 6 * es * B / (pms * 1e-3) / 1e9})
-            print(json.dumps(lines[-1]), flush=True)
+            gbs = 24 * es * B_total / (ms * 1e-3) / 1e9  # aggregate over all ranks
+            lines.append({"kernel_path": m.kernel_path, "dtype": name, "n_gpus": WORLD, "B": B_total, "B_per_gpu": B, "ms": ms, "samples_per_s": B_total / (ms * 1e-3),
+                          "GBps_algorithmic": gbs, "frac_of_measured_hbm": gbs / PEAK / WORLD,
+                          "buffer_sets": nset, "planned_ms": pms, "planned_samples_per_s": B_total / (pms * 1e-3),
+                          "planned_GBps_algorithmic": 6 * es * B_total / (pms * 1e-3) / 1e9})
+            if RANK == 0:
+                print(json.dumps(lines[-1]), flush=True)
             del sets, taus
             torch.cuda.empty_cache()
-    if args.out:
+    if args.out and RANK == 0:
         with open(args.out, "w") as f:
             for ln in lines:
                 f.write(json.dumps(ln) + "\n")
@@ -103,3 +134,5 @@ def main():
 
 if __name__ == "__main__":
     main()
+    if WORLD > 1:
+        torch.distributed.destroy_process_group()
