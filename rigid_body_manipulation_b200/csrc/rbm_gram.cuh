@@ -39,61 +39,6 @@ RBM_HD void gram_accumulate(TA (&acc)[kAcc], const T (&top)[3][4], const T (&bot
   }
 }
 
-// ---- two-way split of the 70 accumulators (warp-pair Gram kernel, rbm_regressor.cu) -----------------------------------------
-// Set 1 = the bottom-block entries among columns 1..8 of W (36 entries, 92 FMAs per sample: they need neither the top block nor
-// the wrench); set 0 = everything else (top block, row 0 of the bottom block, the wrench column: 34 entries, 88 FMAs).
-constexpr int kSetMax = 36;
-__host__ __device__ constexpr int pair_set_bot(int i, int j) { return (i >= 1 && j <= 8) ? 1 : 0; }  // i <= j
-
-template <int SET, class TA, class T>
-RBM_HD void gram_accumulate_set(TA (&acc)[kSetMax], const T (&top)[3][4], const T (&bot)[3][9], const T (&f)[6]) {
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    TA u[5], w[10];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) u[c] = (TA)top[r][c];
-    u[4] = (TA)f[r];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) w[c] = (TA)bot[r][c];
-    w[9] = (TA)f[3 + r];
-    int k = 0;
-    if (SET == 0) {
-#pragma unroll
-      for (int i = 0; i < 5; ++i)
-#pragma unroll
-        for (int j = i; j < 5; ++j) { acc[k] += u[i] * u[j]; ++k; }
-    }
-#pragma unroll
-    for (int i = 0; i < 10; ++i)
-#pragma unroll
-      for (int j = i; j < 10; ++j) {
-        if (pair_set_bot(i, j) == SET) {
-          if (bot_nz(r, i) && bot_nz(r, j)) acc[k] += w[i] * w[j];
-          ++k;
-        }
-      }
-  }
-}
-
-// where entry kglob of the 70-layout lives: (set, index inside that set's accumulator array)
-RBM_HD void pair_locate(int kglob, int& set, int& local) {
-  int k = 0, l0 = 0, l1 = 0;
-  set = 0;
-  local = 0;
-  for (int i = 0; i < 5; ++i)
-    for (int j = i; j < 5; ++j) {
-      if (k == kglob) { set = 0; local = l0; return; }
-      ++k; ++l0;
-    }
-  for (int i = 0; i < 10; ++i)
-    for (int j = i; j < 10; ++j) {
-      const int s_ = pair_set_bot(i, j);
-      if (k == kglob) { set = s_; local = s_ ? l1 : l0; return; }
-      ++k;
-      if (s_) ++l1; else ++l0;
-    }
-}
-
 // Entry t (0..110) of the pack [Y^T Y (100, row-major) | Y^T f (10) | f^T f] from the 70 block accumulators: column 0 of Y lives
 // only in the top block, columns 4..9 only in the bottom block, columns 1..3 in both.
 template <class TA>

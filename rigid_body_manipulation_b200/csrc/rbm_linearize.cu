@@ -27,6 +27,9 @@ constexpr int kLinBlock = 128;
 // Occupancy experiments (tools/kbench `lin`, 2^20 states, 200 launches, G states/s): 2 blocks of 128 threads per SM at 254 registers
 // (this setting) 2.76; 3 blocks at 168 registers (~300 B of spills) 2.69; M^-1 parked in shared memory between the column loops
 // 2.75 with 2 blocks, 2.52 with 3.  More resident warps do not pay for the spills: the setting stays at 2.
+// Round 2: a lane-PAIR version (two lanes share a state: +eps / -eps evaluations, half the M^-1 rows each, 168 or 128 registers, 12 or 16
+// warps per SM) was built, passed the parity suite and LOST: 2.10 / 2.14 against 2.80 G states/s (ncu: +17 % instructions, +14 % DRAM
+// write traffic from half-warp stores, FP64 pipe 46 % instead of 55 %).  Kept as experiments/k_linearize_pair.cu.inc.
 #ifndef RBM_LIN_MINB
 #define RBM_LIN_MINB 2
 #endif

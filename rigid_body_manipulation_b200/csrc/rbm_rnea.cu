@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(kBlock) k_rnea_fast_aos_tma(const __grid_const
                                                               int64_t n) {
   constexpr int S = kAosStages;
   constexpr uint32_t kInBytes = kBlock * 18 * sizeof(T), kOutBytes = kBlock * 6 * sizeof(T);
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  T* in_buf = reinterpret_cast<T*>(smem_raw);                      // [S][kBlock * 18]
+  extern __shared__ __align__(128) unsigned char smem_tiles[];
+  T* in_buf = reinterpret_cast<T*>(smem_tiles);                      // [S][kBlock * 18]
   T* out_buf = in_buf + (size_t)S * kBlock * 18;                   // [2][kBlock * 6]
   __shared__ __align__(8) uint64_t full[S];
   const int tid = threadIdx.x;
