@@ -360,6 +360,8 @@ int analyze_model(const char* who, int nj, const double* hposes_Rt, const double
     J[GJ_WN] = wn;
     for (int k = 0; k < 3; ++k) J[GJ_AXIS + k] = wn > 0.0 ? ax[k] / wn : 0.0;
     std::memcpy(J + GJ_G, simats + 36 * (i + 1), 36 * sizeof(double));
+    RigidForm rf;
+    J[GJ_RIGID] = rigid_form(simats + 36 * (i + 1), &rf) ? 1.0 : 0.0;
   }
   m->gp32.resize(np);
   for (int i = 0; i < np; ++i) m->gp32[i] = (float)g[i];

@@ -35,7 +35,8 @@ enum : int {
   GJ_AXIS = 18,   // w / |w| (3) (zeros when |w| == 0)
   GJ_WN = 21,     // |w| (1)
   GJ_G = 22,      // spatial inertia, dense row-major (36)   simats_body[i+1]
-  GJ_STRIDE = 58
+  GJ_RIGID = 58,  // 1 when G has the rigid-body form [[m 1, -[h]x], [[h]x, Ibar]], Ibar symmetric (then 10 numbers define it), else 0
+  GJ_STRIDE = 59
 };
 static inline int generic_param_count(int nj) { return GP_HEAD + GJ_STRIDE * nj; }
 

@@ -284,6 +284,14 @@ RBM_HD void joint_transform(const T* J /* per-joint param block */, T q, T* R, T
   G3<T> rho = (-q) * g3(J + GJ_S);
   G3<T> ax = g3(J + GJ_AXIS);
   const T wn = J[GJ_WN];
+  if (wn == T(0)) {
+    // pure translation (every sample of a batch takes this branch together: it depends on the model only).  liegroups reaches the same
+    // numbers through its small-angle branch: R = (I + [0]x) M_R, t = rho + 0.5 * 0 x rho.
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = hR[k];
+    p[0] = ht.x + rho.x; p[1] = ht.y + rho.y; p[2] = ht.z + rho.z;
+    return;
+  }
   const T theta = -q * wn;   // signed rotation angle about `ax`
   T E[9], te[3];
   if (abs_t(theta) <= T(1e-8)) {
@@ -378,12 +386,24 @@ RBM_HD void generic_rnea(const T* __restrict__ sp, const T* __restrict__ base /*
     if (tau) {
       const T* G = J + GJ_G;
       T h[6], gd[6];  // momentum G V and inertial force G dV
+      if (J[GJ_RIGID] != T(0)) {
+        // G = [[m 1, -[c]x], [[c]x, I]] (every physical link; warp-uniform branch): 10 numbers instead of a dense 6x6 product
+        const T m = G[0];
+        const G3<T> cm = {G[6 * 5 + 1], G[6 * 3 + 2], G[6 * 4 + 0]};  // first moment m c from the lower-left block [c]x
+        const T I[6] = {G[6 * 3 + 3], G[6 * 4 + 4], G[6 * 5 + 5], G[6 * 3 + 4], G[6 * 4 + 5], G[6 * 5 + 3]};  // xx yy zz xy yz zx
+        auto sym = [&](G3<T> x) -> G3<T> { return {I[0] * x.x + I[3] * x.y + I[5] * x.z, I[3] * x.x + I[1] * x.y + I[4] * x.z, I[5] * x.x + I[4] * x.y + I[2] * x.z}; };
+        const G3<T> hf = m * v + gcross(w, cm), hm = gcross(cm, v) + sym(w);
+        const G3<T> gf = m * a + gcross(l, cm), gm = gcross(cm, a) + sym(l);
+        h[0] = hf.x; h[1] = hf.y; h[2] = hf.z; h[3] = hm.x; h[4] = hm.y; h[5] = hm.z;
+        gd[0] = gf.x; gd[1] = gf.y; gd[2] = gf.z; gd[3] = gm.x; gd[4] = gm.y; gd[5] = gm.z;
+      } else {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        T sh = T(0), sg = T(0);
+        for (int r = 0; r < 6; ++r) {
+          T sh = T(0), sg = T(0);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { sh += G[6 * r + k] * V6[k]; sg += G[6 * r + k] * dV6[k]; }
-        h[r] = sh; gd[r] = sg;
+          for (int k = 0; k < 6; ++k) { sh += G[6 * r + k] * V6[k]; sg += G[6 * r + k] * dV6[k]; }
+          h[r] = sh; gd[r] = sg;
+        }
       }
       // -ad(V)^T [hf; hm] = [w x hf ; v x hf + w x hm]
       G3<T> hf = g3(h), hm = g3(h + 3);

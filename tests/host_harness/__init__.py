@@ -96,7 +96,7 @@ def _model_args(analysis):
     path, fast, generic = analysis
     fp = np.ascontiguousarray(fast, dtype=np.float64)
     gp = np.ascontiguousarray(generic, dtype=np.float64)
-    return C.c_int(PATH_ID[path]), fp, gp, C.c_int((len(gp) - 42) // 58)
+    return C.c_int(PATH_ID[path]), fp, gp, C.c_int((len(gp) - 42) // 59)
 
 
 def linearize(analysis, q, qd, u=None, dt=0.002, eps=1e-8, centered=True):
