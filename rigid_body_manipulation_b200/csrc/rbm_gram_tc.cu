@@ -67,7 +67,7 @@ __device__ __forceinline__ const float* tc_live_stream(int k, const float* q, co
 template <int PATH, bool SEN_DIAG>
 __global__ void __launch_bounds__(kTcBlock, 2) k_regressor_gram_tc(const __grid_constant__ FastParams<float> P, const float* __restrict__ q,
                                                                    const float* __restrict__ qd, const float* __restrict__ qdd,
-                                                                   const float* __restrict__ f, double* __restrict__ partials, int64_t n, int64_t ld, int debug) {
+                                                                   const float* __restrict__ f, double* __restrict__ partials, int64_t n, int64_t ld) {
   constexpr int S = kTcStages;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[S];
@@ -142,15 +142,14 @@ __global__ void __launch_bounds__(kTcBlock, 2) k_regressor_gram_tc(const __grid_
 #pragma unroll 1
       for (int j = 0; j < S; ++j) issue_tma();
     }
-    // debug (timing experiments only, results are then wrong): bit 0 skip the MMAs, bit 1 N = 8, bit 3 M = 128
-    const uint32_t idesc = umma_idesc_tf32((debug & 8) ? 128 : kTcM, (debug & 2) ? 8 : kTcN);
+    const uint32_t idesc = umma_idesc_tf32(kTcM, kTcN);
     const uint64_t desc0 = umma_desc_k_sw128(op_addr, 1024);
     int period = 0;  // local tile index modulo kTcFlush of the tile whose MMAs are issued next
     for (int64_t it = 0; it <= L; ++it) {
       __syncthreads();  // B(it): the operand tiles of local tile it - 1 are complete; the inputs of tile it are in registers
       tc_fence_after_thread_sync();
       if (mma_warp && lane == 0) {
-        if (it > 0 && !(debug & 1)) {  // the tensor core first: the compute warps wait for this commit before they overwrite their operand tiles
+        if (it > 0) {  // the tensor core first: the compute warps wait for this commit before they overwrite their operand tiles
           const uint32_t fresh = period == 0 ? 0u : 1u;  // first tile of a flush period overwrites the accumulator
 #pragma unroll
           for (int w = 0; w < kTcComputeWarps; ++w) {
@@ -170,8 +169,6 @@ __global__ void __launch_bounds__(kTcBlock, 2) k_regressor_gram_tc(const __grid_
               }
             }
           }
-        }
-        if (it > 0) {
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(done_addr) : "memory");
           period = period == kTcFlush - 1 ? 0 : period + 1;
         }
@@ -349,7 +346,6 @@ int tc_gram_grid(int sms, int64_t n) {
 int launch_regressor_gram_tc(const rbm_model* m, const float* q, const float* qd, const float* qdd, const float* f, double* partials, int64_t n, int64_t ld,
                              int grid, cudaStream_t st) {
   const FastParams<float>& P = ModelView<float>::fast(m);
-  static const int debug = [] { const char* e = getenv("RBM_TC_DEBUG"); return e ? atoi(e) : 0; }();
   const bool diag = P.sen_diag != 0.f;
   const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
   static std::atomic<bool> attr_set[64];
@@ -361,11 +357,11 @@ int launch_regressor_gram_tc(const rbm_model* m, const float* q, const float* qd
     attr_set[dev].store(true, std::memory_order_release);
   }
   if (m->path == PATH_SEQ_ISO) {
-    if (diag) k_regressor_gram_tc<PATH_SEQ_ISO, true><<<grid, kTcBlock, kTcSmemBytes, st>>>(P, q, qd, qdd, f, partials, n, ld, debug);
-    else k_regressor_gram_tc<PATH_SEQ_ISO, false><<<grid, kTcBlock, kTcSmemBytes, st>>>(P, q, qd, qdd, f, partials, n, ld, debug);
+    if (diag) k_regressor_gram_tc<PATH_SEQ_ISO, true><<<grid, kTcBlock, kTcSmemBytes, st>>>(P, q, qd, qdd, f, partials, n, ld);
+    else k_regressor_gram_tc<PATH_SEQ_ISO, false><<<grid, kTcBlock, kTcSmemBytes, st>>>(P, q, qd, qdd, f, partials, n, ld);
   } else {
-    if (diag) k_regressor_gram_tc<PATH_SEQ_RIGID, true><<<grid, kTcBlock, kTcSmemBytes, st>>>(P, q, qd, qdd, f, partials, n, ld, debug);
-    else k_regressor_gram_tc<PATH_SEQ_RIGID, false><<<grid, kTcBlock, kTcSmemBytes, st>>>(P, q, qd, qdd, f, partials, n, ld, debug);
+    if (diag) k_regressor_gram_tc<PATH_SEQ_RIGID, true><<<grid, kTcBlock, kTcSmemBytes, st>>>(P, q, qd, qdd, f, partials, n, ld);
+    else k_regressor_gram_tc<PATH_SEQ_RIGID, false><<<grid, kTcBlock, kTcSmemBytes, st>>>(P, q, qd, qdd, f, partials, n, ld);
   }
   RBM_CUDA_TRY(cudaGetLastError());
   return RBM_OK;
