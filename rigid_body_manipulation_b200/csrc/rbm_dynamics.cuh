@@ -64,6 +64,19 @@ struct FastEval {
 #pragma unroll
     for (int k = 0; k < 6; ++k) tau[k] = r.tau[k];
   }
+  // column J of the inertia matrix with the other joint accelerations as structural zeros (fast_rnea_core, ONEHOT)
+  template <int J>
+  RBM_HD void inertia_col(const T (&q)[6], const T (&c)[6], const T (&s)[6], T (&M)[6][6]) const {
+    FastResult<T> r;
+    fast_rnea_core<T, D, true, false, false, true, J>(P, P.g, q, c, s, q /* unused */, q /* unused */, r);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) M[k][J] = r.tau[k];
+  }
+  // joint-space inertia matrix M(q), column by column
+  RBM_HD void inertia_matrix(const T (&q)[6], const T (&c)[6], const T (&s)[6], T (&M)[6][6]) const {
+    inertia_col<0>(q, c, s, M); inertia_col<1>(q, c, s, M); inertia_col<2>(q, c, s, M);
+    inertia_col<3>(q, c, s, M); inertia_col<4>(q, c, s, M); inertia_col<5>(q, c, s, M);
+  }
 };
 
 template <class T>
@@ -101,6 +114,20 @@ struct GenericEval {
 #pragma unroll
     for (int k = 0; k < MAXJ; ++k) qd0[k] = T(0);
     generic_rnea<T, 0>(sp, zero, nj_, q, qd0, qdd, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
+  }
+  RBM_HD void inertia_matrix(const T (&q)[MAXJ], const T (&c)[MAXJ], const T (&s)[MAXJ], T (&M)[MAXJ][MAXJ]) const {
+#pragma unroll 1
+    for (int j = 0; j < nj_; ++j) {
+      T e[MAXJ], col[MAXJ];
+#pragma unroll
+      for (int k = 0; k < MAXJ; ++k) e[k] = (k == j) ? T(1) : T(0);
+      id_inertia(q, c, s, e, col);
+#pragma unroll
+      for (int r = 0; r < MAXJ; ++r)
+#pragma unroll
+        for (int k = 0; k < MAXJ; ++k)
+          if (k == j) M[r][k] = col[r];
+    }
   }
 };
 
@@ -218,18 +245,7 @@ RBM_HD void linearize_state(const E& ev, const T* __restrict__ q_in, const T* __
 
   // joint-space inertia matrix, column by column
   T M[MJ][MJ];
-#pragma unroll 1
-  for (int j = 0; j < nj; ++j) {
-    T e[MJ], col[MJ];
-#pragma unroll
-    for (int k = 0; k < MJ; ++k) e[k] = (k == j) ? T(1) : T(0);
-    ev.id_inertia(q, c, sn, e, col);
-#pragma unroll
-    for (int r = 0; r < MJ; ++r)
-#pragma unroll
-      for (int k = 0; k < MJ; ++k)
-        if (k == j) M[r][k] = col[r];
-  }
+  ev.inertia_matrix(q, c, sn, M);
   // bias forces and nominal acceleration
   T h[MJ], qdd[MJ];
   ev.id(q, c, sn, qd, zero, h);
@@ -409,18 +425,7 @@ RBM_HD void forward_dynamics_state(const E& ev, const T* __restrict__ q_in, cons
   }
   ev.trig(q, c, sn);
   T M[MJ][MJ];
-#pragma unroll 1
-  for (int j = 0; j < nj; ++j) {
-    T e[MJ], col[MJ];
-#pragma unroll
-    for (int k = 0; k < MJ; ++k) e[k] = (k == j) ? T(1) : T(0);
-    ev.id_inertia(q, c, sn, e, col);
-#pragma unroll
-    for (int r = 0; r < MJ; ++r)
-#pragma unroll
-      for (int k = 0; k < MJ; ++k)
-        if (k == j) M[r][k] = col[r];
-  }
+  ev.inertia_matrix(q, c, sn, M);
   T h[MJ], qdd[MJ];
   ev.id(q, c, sn, qd, zero, h);
   cholesky<T, MJ>(M, nj);
@@ -483,18 +488,7 @@ RBM_HD void closed_loop_env(const E& ev, const PlanArg<T>& pl, const T* __restri
     ev.trig(q, c, sn);
     {
       T M[MJ][MJ];
-#pragma unroll 1
-      for (int j = 0; j < nj; ++j) {
-        T e[MJ], col[MJ];
-#pragma unroll
-        for (int k = 0; k < MJ; ++k) e[k] = (k == j) ? T(1) : T(0);
-        ev.id_inertia(q, c, sn, e, col);
-#pragma unroll
-        for (int r = 0; r < MJ; ++r)
-#pragma unroll
-          for (int k = 0; k < MJ; ++k)
-            if (k == j) M[r][k] = col[r];
-      }
+      ev.inertia_matrix(q, c, sn, M);
       T h[MJ];
       ev.id(q, c, sn, qd, zero, h);
       cholesky<T, MJ>(M, nj);

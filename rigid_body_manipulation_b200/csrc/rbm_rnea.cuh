@@ -179,7 +179,7 @@ RBM_HD void fast_sincos(const T (&q)[6], T (&c)[6], T (&s)[6]) {
   }
 }
 
-template <class T, class D, bool WANT_TAU, bool VEL = true, bool GRAV = true, bool ACC = true>
+template <class T, class D, bool WANT_TAU, bool VEL = true, bool GRAV = true, bool ACC = true, int ONEHOT = -1>
 RBM_HD void fast_rnea_core(const FastParams<T>& P, const T* g, const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6],
                            const T (&qdd)[6], FastResult<T>& out);
 
@@ -202,8 +202,10 @@ RBM_HD void fast_rnea(const FastParams<T>& P, const T (&q)[6], const T (&qd)[6],
 // matrix is being extracted column by column).
 // VEL = false treats every joint velocity as a structural zero, GRAV = false the base acceleration and ACC = false every joint
 // acceleration: (VEL off, GRAV off) is the acceleration-only evaluation whose columns are the joint-space inertia matrix,
-// (ACC off, GRAV off) the velocity-product term C(q, qd) alone.
-template <class T, class D, bool WANT_TAU, bool VEL, bool GRAV, bool ACC>
+// (ACC off, GRAV off) the velocity-product term C(q, qd) alone.  ONEHOT = j >= 0 (with VEL and GRAV off) evaluates qdd = e_j with every
+// other joint acceleration a STRUCTURAL zero: column j of the inertia matrix, where the links before j carry no motion at all and the
+// typed algebra removes their share of the recursion (the linearisation builds M this way: about half the work of six general columns).
+template <class T, class D, bool WANT_TAU, bool VEL, bool GRAV, bool ACC, int ONEHOT>
 RBM_HD void fast_rnea_core(const FastParams<T>& P, const T* g, const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6],
                            const T (&qdd)[6], FastResult<T>& out) {
   // base: twist_0 = 0, dtwist_0 = [g; 0]  (core/simulate.py:149,154-155)
@@ -218,16 +220,21 @@ RBM_HD void fast_rnea_core(const FastParams<T>& P, const T* g, const T (&q)[6], 
     if constexpr (VEL) return qd[i];
     else return Z{};
   };
-  auto acc = [&](int i) {
-    if constexpr (ACC) return qdd[i];
+  auto acc = [&](auto I) {
+    constexpr int i = decltype(I)::value;
+    if constexpr (ONEHOT >= 0) {
+      if constexpr (i == ONEHOT) return T(1);
+      else return Z{};
+    } else if constexpr (ACC) return qdd[i];
     else return Z{};
   };
-  auto k0 = fwd_link<typename D::L0, 0>(P, q[0], vel(0), acc(0), c[0], s[0], v0, w0, a0, l0);
-  auto k1 = fwd_link<typename D::L1, 1>(P, q[1], vel(1), acc(1), c[1], s[1], k0.v, k0.w, k0.a, k0.l);
-  auto k2 = fwd_link<typename D::L2, 2>(P, q[2], vel(2), acc(2), c[2], s[2], k1.v, k1.w, k1.a, k1.l);
-  auto k3 = fwd_link<typename D::L3, 3>(P, q[3], vel(3), acc(3), c[3], s[3], k2.v, k2.w, k2.a, k2.l);
-  auto k4 = fwd_link<typename D::L4, 4>(P, q[4], vel(4), acc(4), c[4], s[4], k3.v, k3.w, k3.a, k3.l);
-  auto k5 = fwd_link<typename D::L5, 5>(P, q[5], vel(5), acc(5), c[5], s[5], k4.v, k4.w, k4.a, k4.l);
+  using std::integral_constant;
+  auto k0 = fwd_link<typename D::L0, 0>(P, q[0], vel(0), acc(integral_constant<int, 0>{}), c[0], s[0], v0, w0, a0, l0);
+  auto k1 = fwd_link<typename D::L1, 1>(P, q[1], vel(1), acc(integral_constant<int, 1>{}), c[1], s[1], k0.v, k0.w, k0.a, k0.l);
+  auto k2 = fwd_link<typename D::L2, 2>(P, q[2], vel(2), acc(integral_constant<int, 2>{}), c[2], s[2], k1.v, k1.w, k1.a, k1.l);
+  auto k3 = fwd_link<typename D::L3, 3>(P, q[3], vel(3), acc(integral_constant<int, 3>{}), c[3], s[3], k2.v, k2.w, k2.a, k2.l);
+  auto k4 = fwd_link<typename D::L4, 4>(P, q[4], vel(4), acc(integral_constant<int, 4>{}), c[4], s[4], k3.v, k3.w, k3.a, k3.l);
+  auto k5 = fwd_link<typename D::L5, 5>(P, q[5], vel(5), acc(integral_constant<int, 5>{}), c[5], s[5], k4.v, k4.w, k4.a, k4.l);
 
   out.v[0] = to_scalar<T>(k5.v.x); out.v[1] = to_scalar<T>(k5.v.y); out.v[2] = to_scalar<T>(k5.v.z);
   out.w[0] = to_scalar<T>(k5.w.x); out.w[1] = to_scalar<T>(k5.w.y); out.w[2] = to_scalar<T>(k5.w.z);
