@@ -64,6 +64,13 @@ struct FastEval {
 #pragma unroll
     for (int k = 0; k < 6; ++k) tau[k] = r.tau[k];
   }
+  // bias forces h(q, qd) = ID(q, qd, 0): joint accelerations as structural zeros
+  RBM_HD void id_bias(const T (&q)[6], const T (&c)[6], const T (&s)[6], const T (&qd)[6], T (&tau)[6]) const {
+    FastResult<T> r;
+    fast_rnea_core<T, D, true, true, true, false>(P, P.g, q, c, s, qd, qd /* unused */, r);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tau[k] = r.tau[k];
+  }
   // column J of the inertia matrix with the other joint accelerations as structural zeros (fast_rnea_core, ONEHOT)
   template <int J>
   RBM_HD void inertia_col(const T (&q)[6], const T (&c)[6], const T (&s)[6], T (&M)[6][6]) const {
@@ -114,6 +121,12 @@ struct GenericEval {
 #pragma unroll
     for (int k = 0; k < MAXJ; ++k) qd0[k] = T(0);
     generic_rnea<T, 0>(sp, zero, nj_, q, qd0, qdd, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
+  }
+  RBM_HD void id_bias(const T (&q)[MAXJ], const T (&c)[MAXJ], const T (&s)[MAXJ], const T (&qd)[MAXJ], T (&tau)[MAXJ]) const {
+    T qdd0[MAXJ];
+#pragma unroll
+    for (int k = 0; k < MAXJ; ++k) qdd0[k] = T(0);
+    id(q, c, s, qd, qdd0, tau);
   }
   RBM_HD void inertia_matrix(const T (&q)[MAXJ], const T (&c)[MAXJ], const T (&s)[MAXJ], T (&M)[MAXJ][MAXJ]) const {
 #pragma unroll 1
@@ -248,7 +261,7 @@ RBM_HD void linearize_state(const E& ev, const T* __restrict__ q_in, const T* __
   ev.inertia_matrix(q, c, sn, M);
   // bias forces and nominal acceleration
   T h[MJ], qdd[MJ];
-  ev.id(q, c, sn, qd, zero, h);
+  ev.id_bias(q, c, sn, qd, h);
   cholesky<T, MJ>(M, nj);
   // fast path (nj fixed at compile time): explicit M^-1 once, then mat-vecs; generic path: one pair of triangular sweeps per
   // right-hand side (a fully unrolled 16 x 16 inverse would not fit in registers)
@@ -427,7 +440,7 @@ RBM_HD void forward_dynamics_state(const E& ev, const T* __restrict__ q_in, cons
   T M[MJ][MJ];
   ev.inertia_matrix(q, c, sn, M);
   T h[MJ], qdd[MJ];
-  ev.id(q, c, sn, qd, zero, h);
+  ev.id_bias(q, c, sn, qd, h);
   cholesky<T, MJ>(M, nj);
 #pragma unroll
   for (int k = 0; k < MJ; ++k) qdd[k] = u[k] - h[k];
@@ -490,7 +503,7 @@ RBM_HD void closed_loop_env(const E& ev, const PlanArg<T>& pl, const T* __restri
       T M[MJ][MJ];
       ev.inertia_matrix(q, c, sn, M);
       T h[MJ];
-      ev.id(q, c, sn, qd, zero, h);
+      ev.id_bias(q, c, sn, qd, h);
       cholesky<T, MJ>(M, nj);
 #pragma unroll
       for (int k = 0; k < MJ; ++k) qacc[k] = u[k] - h[k];

@@ -221,11 +221,10 @@ RBM_HD void fast_rnea_core(const FastParams<T>& P, const T* g, const T (&q)[6], 
     else return Z{};
   };
   auto acc = [&](auto I) {
-    constexpr int i = decltype(I)::value;
     if constexpr (ONEHOT >= 0) {
-      if constexpr (i == ONEHOT) return T(1);
+      if constexpr (decltype(I)::value == ONEHOT) return T(1);
       else return Z{};
-    } else if constexpr (ACC) return qdd[i];
+    } else if constexpr (ACC) return qdd[decltype(I)::value];
     else return Z{};
   };
   using std::integral_constant;

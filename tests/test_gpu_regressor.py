@@ -266,3 +266,32 @@ def test_tensor_core_gram_identifies_like_the_register_kernel():
         assert est[name].rank == 10
         assert (np.abs(est[name].phi - phi_true) / scale).max() < 2e-3
     assert (np.abs(est["tc"].phi - est["reg"].phi) / scale).max() < 2e-3
+
+
+@pytest.mark.parametrize("dtype,tc,tol", [(torch.float64, False, 1e-12), (torch.float32, False, 2e-6), (torch.float32, True, 5e-5)])
+def test_gram_is_additive_at_the_configs2_size(dtype, tc, tol):
+    """BASELINE configs[2] per-GPU share (12.5 M samples), size-independent properties: the pack of the whole batch equals the sum of the
+    packs of its two halves (what the multi-GPU all-reduce relies on), the sample count is exact, and a batch that is the same 4096
+    samples repeated gives 3052 x the pack of one copy (+ the ragged remainder), so every tile of the persistent grid is accounted for."""
+    g = load_golden("ref_inverse_uniform_gearbox.npz")
+    m = model_from_golden(g, gram_tensor_cores=tc)
+    n = 12_500_000
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    q = (torch.rand((6, n), generator=gen, device="cuda", dtype=dtype) * 2 - 1) * 6
+    qd = torch.randn((6, n), generator=gen, device="cuda", dtype=dtype)
+    qdd = torch.randn((6, n), generator=gen, device="cuda", dtype=dtype) * 3
+    f = torch.randn((6, n), generator=gen, device="cuda", dtype=dtype) * 2
+    whole = m.regressor_gram(q, qd, qdd, f).cpu().numpy()
+    h = 6_250_240  # a multiple of 256 so that both halves stay on the TMA path (16-byte aligned row starts)
+    halves = sum(m.regressor_gram(*(t[:, a:b].contiguous() for t in (q, qd, qdd, f))).cpu().numpy() for a, b in ((0, h), (h, n)))
+    scale = np.abs(whole[:100]).max()
+    assert whole[111] == n and halves[111] == n
+    assert np.abs(whole[:111] - halves[:111]).max() < tol * scale
+    # periodic batch: 4096 distinct samples tiled over the whole 12.5 M
+    reps, rem = divmod(n, 4096)
+    tile = lambda t: t[:, :4096].repeat(1, reps + 1)[:, :n].contiguous()
+    per = m.regressor_gram(tile(q), tile(qd), tile(qdd), tile(f)).cpu().numpy()
+    one = m.regressor_gram(*(t[:, :4096].contiguous() for t in (q, qd, qdd, f))).cpu().numpy()
+    tail = m.regressor_gram(*(t[:, :rem].contiguous() for t in (q, qd, qdd, f))).cpu().numpy() if rem else 0.0
+    expect = reps * one + tail
+    assert np.abs(per[:111] - expect[:111]).max() < max(tol, 1e-11) * np.abs(expect[:100]).max() * (50 if dtype == torch.float32 else 1)

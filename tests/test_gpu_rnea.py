@@ -299,3 +299,26 @@ def test_fp32_soa_sizes_and_flags(n, no_tma):
     assert rel_err(tau_aos.cpu().numpy(), ref).max() < TOL32
     tau_aos64 = m.rnea_aos(torch.as_tensor(traj, device="cuda"))
     assert rel_err(tau_aos64.cpu().numpy(), ref).max() < TOL64
+
+
+def test_full_size_properties_of_configs1():
+    """BASELINE configs[1] at its full size (2^20 samples, fp64) through properties that need no oracle run: tau is affine in qdd at
+    fixed (q, qd) -- tau(qdd1 + qdd2) - tau(qdd1) - tau(qdd2) + tau(0) = 0 --, independent of the gantry positions (the rows the kernel
+    never loads), and the SoA, AoS and host entry points agree on every sample."""
+    g = load_golden("ref_inverse_hammer.npz")
+    m = model_from_golden(g)
+    n = 1 << 20
+    traj = sample_states(np.random.default_rng(21), n)
+    q, qd, qdd = soa(traj)
+    z = torch.zeros_like(qdd)
+    qdd2 = torch.roll(qdd, 1, dims=1)
+    t12, t1, t2, t0 = m.rnea(q, qd, qdd + qdd2), m.rnea(q, qd, qdd), m.rnea(q, qd, qdd2), m.rnea(q, qd, z)
+    resid = (t12 - t1 - t2 + t0).abs().max().item()
+    assert resid < 1e-10 * t12.abs().max().item()
+    moved = q.clone()
+    moved[:3] += 7.25
+    assert torch.equal(m.rnea(moved, qd, qdd), t1)                      # bit-identical: those rows are not read
+    dev = torch.as_tensor(traj, device="cuda")
+    assert rel_err(m.rnea_aos(dev).cpu().numpy(), t1.t().cpu().numpy()).max() < 1e-13
+    host = m.rnea_host_soa(*(np.ascontiguousarray(traj[:, k, :].T) for k in range(3)))
+    assert np.array_equal(host, t1.cpu().numpy())                       # same kernel behind the host entry
