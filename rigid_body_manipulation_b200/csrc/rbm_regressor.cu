@@ -223,12 +223,12 @@ __global__ void __launch_bounds__(kGramBlock, 1) k_regressor_gram(const __grid_c
   gram_block_epilogue<T>(acc, red, partials);
 }
 
-// ---- pipelined variant (fast paths): TMA bulk copies stage whole 256-sample tiles of the LIVE input streams (21 x 2 KB in fp64) into
+// ---- pipelined variant (fast paths): TMA bulk copies stage whole 512-sample tiles of the LIVE input streams (21 x 4 KB in fp64) into
 // shared memory kPipeStages tiles ahead of the arithmetic, so the loads never wait on registers or occupancy.
 // Only live streams are staged: V_6 and dV_6 of the sequential structure do not depend on the three gantry positions
 // (SequentialDesc::q_matters), so q[0..2] are never read -- 21 bulk copies per tile instead of 24, 168 instead of 192 B of DRAM traffic per
-// fp64 sample (ncu: 2.10 GB instead of 2.40 GB per 12.5 M samples), and the smaller tile buys a fifth stage.  The issue cost of a bulk
-// copy is paid by the issuing warp, so the 21 copies are spread over the 8 warps with their source pointers formed once.
+// fp64 sample (ncu: 2.10 GB instead of 2.40 GB per 12.5 M samples).  The issue cost of a bulk copy is paid by the issuing warp, so the
+// 21 copies are spread over the 8 warps with their source pointers formed once.
 // What was measured on B200 on the way here (12.5 M samples, G samples/s fp64 / fp32, burst clocks; logs under profiles/):
 //   round 1  direct global loads                                      23.6 / 25.0   (41 % of stall samples on the load scoreboard)
 //            TMA, one elected thread issues all 24 copies             21.8 / 34.9   (the issuing warp pays ~24 x UBLKCP per tile)
@@ -236,15 +236,18 @@ __global__ void __launch_bounds__(kGramBlock, 1) k_regressor_gram(const __grid_c
 //            per-warp pipelines with 256-byte copies                  17.6 / 26.5   (8x more copies: TMA-issue bound)
 //            TMA, 24 copies spread over the 8 warps                   29.9 / 47.0   (round-1 production kernel)
 //            per-stage empty mbarriers / warp-specialised split / FFMA2 accumulators: all slower (experiments/README.md)
-//   round 2  live streams only, 5 stages (THIS KERNEL)                31.3 / 47.3
+//   round 2  live streams only, 256-sample tiles, 5 stages            31.3 / 47.6   (experiments/k_regressor_gram_tma_1spt.cu.inc)
 //            + software-pipelined accumulation (sample i's 180 FMAs issued with sample i + 1's kinematic chain in one basic block)
 //                                                                     28.2 / 44.2   (ptxas front-loads the FMAs; +14 % instructions)
 //            warp-pair split of the 70 accumulators (12 warps / SM, 162 registers, 17 % more FP64 work)   29.9 / 43.2
+//            dedicated TMA producer warpgroup, consumers without a CTA barrier                              30.1 /  --
 //            fp32 on the tensor cores (tcgen05 tf32 hi/lo, rbm_gram_tc.cu)                                   -- / 34.5
-// ncu of this kernel (profiles/r2_gram_v2_ncu_full.csv, r2_gram32_v2_ncu_full.csv): fp64 FP64 pipe 60 % active, issue slots 49 %, 8 warps
-// per SM at 239 registers; fp32 issue slots 75 % busy, FMA pipe 47 %, 16 warps per SM.
+//            512-sample tiles, two samples per thread, 2 stages (THIS KERNEL)                              33.6 / 54.9
+// ncu of the 256-sample kernel (profiles/r2_gram_v2_ncu_full.csv, r2_gram32_v2_ncu_full.csv): fp64 FP64 pipe 60 % active, issue slots 49 %,
+// 19 % of the loop's stall samples in the per-tile hand-over; fp32 issue slots 75 % busy -- which is what the larger tile attacks.
 constexpr int kLiveStreams = 21;  // q3..5 (3) | qd (6) | qdd (6) | f (6)
-constexpr int kPipeStages = 5;
+constexpr int kTmaTile = 2 * kGramBlock;  // samples per tile: two per thread
+constexpr int kPipeStages = 2;
 
 template <class T>
 struct GramCarry {
@@ -289,30 +292,31 @@ __device__ __forceinline__ const T* live_stream(int k, const T* q, const T* qd, 
   return k < 3 ? q + (int64_t)(3 + k) * ld : k < 9 ? qd + (int64_t)(k - 3) * ld : k < 15 ? qdd + (int64_t)(k - 9) * ld : f + (int64_t)(k - 15) * ld;
 }
 
+// Each thread takes TWO samples of a 512-sample tile (tid and tid + 256) and reads them straight from the stage, which is handed back
+// after the arithmetic: the per-tile work every thread repeats (mbarrier wait, CTA barrier, copy issue, loop control: ~100 of the fp32
+// kernel's 523 instructions per sample) is paid once per two samples, and there is no copy of the inputs to registers first.  Two
+// stages of 21 x 512 values (fp64: 2 x 86 KB, one CTA per SM; fp32: 2 x 43 KB, two CTAs per SM).
 template <class T, int PATH, bool SEN_DIAG>
 __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regressor_gram_tma(const __grid_constant__ FastParams<T> P, const T* __restrict__ q,
-                                                                                             const T* __restrict__ qd, const T* __restrict__ qdd,
-                                                                                             const T* __restrict__ f, double* __restrict__ partials,
-                                                                                             int64_t n, int64_t ld) {
+                                                                                              const T* __restrict__ qd, const T* __restrict__ qdd,
+                                                                                              const T* __restrict__ f, double* __restrict__ partials,
+                                                                                              int64_t n, int64_t ld) {
   constexpr int S = kPipeStages;
   constexpr int NW = kGramBlock / 32;
-  constexpr uint32_t kRowBytes = kGramBlock * sizeof(T);
+  constexpr uint32_t kRowBytes = kTmaTile * sizeof(T);
   extern __shared__ __align__(128) unsigned char smem_stages[];
-  T* buf = reinterpret_cast<T*>(smem_stages);  // [S][kLiveStreams][kGramBlock]
+  T* buf = reinterpret_cast<T*>(smem_stages);  // [S][kLiveStreams][512]
   __shared__ __align__(8) uint64_t full[S];
   __shared__ double red[NW][kAcc];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t nfull = n / kGramBlock;  // tiles moved by bulk copies; a ragged tail tile is read directly
+  const int64_t nfull = n / kTmaTile;
   for (int k = lane; k < kAcc; k += 32) red[warp][k] = 0.0;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < S; ++s) mbar_init(&full[s], NW);  // one arrive.expect_tx per warp (its share of the 21 copies)
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], NW);
     mbar_init_fence();
   }
   __syncthreads();
-
-  // The issue cost of a bulk copy is paid by the issuing warp: lane 0 of warp w brings streams w, w + 8, w + 16 (< 21).  Their
-  // source rows are fixed for the whole kernel, so the pointers are formed once.
   const int my_copies = (warp + 2 * NW < kLiveStreams) ? 3 : 2;
   const T* my_src[3];
 #pragma unroll
@@ -323,68 +327,74 @@ __global__ void __launch_bounds__(kGramBlock, sizeof(T) == 4 ? 2 : 1) k_regresso
     const int st = (int)(it % S);
     uint64_t* bar = &full[st];
     mbar_arrive_expect_tx(bar, my_copies * kRowBytes);
-    T* dst = buf + ((size_t)st * kLiveStreams + warp) * kGramBlock;
-    const int64_t s0 = tile * kGramBlock;
+    T* dst = buf + ((size_t)st * kLiveStreams + warp) * kTmaTile;
+    const int64_t s0 = tile * kTmaTile;
     bulk_copy_g2s(dst, my_src[0] + s0, kRowBytes, bar);
-    bulk_copy_g2s(dst + NW * kGramBlock, my_src[1] + s0, kRowBytes, bar);
-    if (my_copies == 3) bulk_copy_g2s(dst + 2 * NW * kGramBlock, my_src[2] + s0, kRowBytes, bar);
+    bulk_copy_g2s(dst + NW * kTmaTile, my_src[1] + s0, kRowBytes, bar);
+    if (my_copies == 3) bulk_copy_g2s(dst + 2 * NW * kTmaTile, my_src[2] + s0, kRowBytes, bar);
   };
   if (lane == 0) {
     for (int it = 0; it < S; ++it) issue(it);
   }
-
   T acc[kAcc];
 #pragma unroll
   for (int k = 0; k < kAcc; ++k) acc[k] = T(0);
+  auto sample = [&](const T* src, int stride) {  // one sample whose 21 values sit `stride` apart starting at src
+    T rq[6], rqd[6], rqdd[6], c[6], sn[6];
+    GramCarry<T> z;
+    rq[0] = rq[1] = rq[2] = T(0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rq[3 + k] = src[k * stride];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      rqd[k] = src[(3 + k) * stride];
+      rqdd[k] = src[(9 + k) * stride];
+      z.f[k] = src[(15 + k) * stride];
+    }
+    fast_sincos<T, SeqIso>(rq, c, sn);
+    gram_kinematics_cs<T, PATH, SEN_DIAG>(P, rq, c, sn, rqd, rqdd, z);
+    gram_accumulate_carry(acc, z);
+  };
   int since_flush = 0;
   for (int64_t it = 0;; ++it) {
     const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
     if (tile >= nfull) break;
     const int st = (int)(it % S);
     mbar_wait(&full[st], (uint32_t)((it / S) & 1));
-    const T* src = buf + (size_t)st * kLiveStreams * kGramBlock + tid;
-    T rq[6], rqd[6], rqdd[6];
-    GramCarry<T> zn;
-    rq[0] = rq[1] = rq[2] = T(0);  // dead inputs of the sequential structure
-#pragma unroll
-    for (int k = 0; k < 3; ++k) rq[3 + k] = src[k * kGramBlock];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      rqd[k] = src[(3 + k) * kGramBlock];
-      rqdd[k] = src[(9 + k) * kGramBlock];
-      zn.f[k] = src[(15 + k) * kGramBlock];
-    }
-    __syncthreads();               // every thread holds its sample in registers: the stage can be refilled
-    if (lane == 0) issue(it + S);  // each warp re-issues its streams
-    T c[6], s[6];
-    fast_sincos<T, SeqIso>(rq, c, s);
-    gram_kinematics_cs<T, PATH, SEN_DIAG>(P, rq, c, s, rqd, rqdd, zn);
-    gram_accumulate_carry(acc, zn);
+    const T* src = buf + (size_t)st * kLiveStreams * kTmaTile + tid;
+    sample(src, kTmaTile);
+    sample(src + kGramBlock, kTmaTile);
     if constexpr (sizeof(T) == 4) {
-      if (++since_flush == kFlush) {
+      since_flush += 2;
+      if (since_flush >= kFlush) {
         since_flush = 0;
         gram_flush_f32(acc, red[warp], lane);
       }
     }
+    __syncthreads();               // everybody is done with the stage
+    if (lane == 0) issue(it + S);  // refill it with the tile two ahead (the other stage is already loading / loaded)
   }
-  // ragged tail (n % 256 samples): owned by the CTA that would have received tile `nfull`
+  // ragged tail (n % 512 samples): owned by the CTA that would have received tile `nfull`
   if ((nfull % gridDim.x) == blockIdx.x) {
-    const int64_t s = nfull * kGramBlock + tid;
-    if (s < n) {
-      T rq[6], rqd[6], rqdd[6], c[6], sn[6];
-      GramCarry<T> z;
-      rq[0] = rq[1] = rq[2] = T(0);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const int64_t s = nfull * kTmaTile + h * kGramBlock + tid;
+      if (s < n) {
+        T rq[6], rqd[6], rqdd[6], c[6], sn[6];
+        GramCarry<T> z;
+        rq[0] = rq[1] = rq[2] = T(0);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) rq[3 + k] = __ldg(q + (3 + k) * ld + s);
+        for (int k = 0; k < 3; ++k) rq[3 + k] = __ldg(q + (3 + k) * ld + s);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        rqd[k] = __ldg(qd + k * ld + s);
-        rqdd[k] = __ldg(qdd + k * ld + s);
-        z.f[k] = __ldg(f + k * ld + s);
+        for (int k = 0; k < 6; ++k) {
+          rqd[k] = __ldg(qd + k * ld + s);
+          rqdd[k] = __ldg(qdd + k * ld + s);
+          z.f[k] = __ldg(f + k * ld + s);
+        }
+        fast_sincos<T, SeqIso>(rq, c, sn);
+        gram_kinematics_cs<T, PATH, SEN_DIAG>(P, rq, c, sn, rqd, rqdd, z);
+        gram_accumulate_carry(acc, z);
       }
-      fast_sincos<T, SeqIso>(rq, c, sn);
-      gram_kinematics_cs<T, PATH, SEN_DIAG>(P, rq, c, sn, rqd, rqdd, z);
-      gram_accumulate_carry(acc, z);
     }
   }
   gram_block_epilogue<T>(acc, red, partials);
@@ -527,7 +537,7 @@ int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* 
   if (n > 0) {
     // bulk copies need 16-byte aligned rows: base pointers and the row pitch
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    const bool tma_ok = m->path != PATH_GENERIC && al16(q) && al16(qd) && al16(qdd) && al16(f) && ((ld * sizeof(T)) % 16 == 0) && n >= kGramBlock &&
+    const bool tma_ok = m->path != PATH_GENERIC && al16(q) && al16(qd) && al16(qdd) && al16(f) && ((ld * sizeof(T)) % 16 == 0) && n >= kTmaTile &&
                         !m->no_tma;
     const int dev = (m->device >= 0 && m->device < 64) ? m->device : 0;
     const bool diag = P.sen_diag != T(0);
@@ -542,8 +552,10 @@ int launch_regressor_gram(const rbm_model* m, const T* q, const T* qd, const T* 
       }
     }
     if (tma_ok) {
-      grid = gram_grid(m, n, sizeof(T) == 4 ? 2 : 1);  // fp32: 125 registers, 105 KB of stages: two CTAs per SM
-      constexpr size_t smem = (size_t)kPipeStages * kLiveStreams * kGramBlock * sizeof(T);
+      const int64_t tiles = n / kTmaTile;  // the ragged tail rides with the CTA that would have received the next tile
+      const int64_t cap = (int64_t)sm_count(m->device) * (sizeof(T) == 4 ? 2 : 1);  // fp64 254 registers: 1 CTA / SM; fp32 128: 2
+      grid = (int)(tiles < cap ? tiles : cap);
+      constexpr size_t smem = (size_t)kPipeStages * kLiveStreams * kTmaTile * sizeof(T);
       auto kfn = m->path == PATH_SEQ_ISO ? (diag ? k_regressor_gram_tma<T, PATH_SEQ_ISO, true> : k_regressor_gram_tma<T, PATH_SEQ_ISO, false>)
                                          : (diag ? k_regressor_gram_tma<T, PATH_SEQ_RIGID, true> : k_regressor_gram_tma<T, PATH_SEQ_RIGID, false>);
       static std::atomic<const void*> ready[64][4];  // the dynamic shared-memory limit is a per-device function attribute: raised once

@@ -10,7 +10,7 @@ SOURCES = {
     # of earlier launches' tau are part of what each launch moves
     "rnea_f64_1048576": "r2_rnea_f64_steady_ncu_full.csv",
     "rnea_f32_1048576": "r1c_rnea_f32_ncu_full.csv",
-    "gram_f64_12500000": "r2_gram_v2_ncu_full.csv",
+    "gram_f64_12500000": "r2_gram_v3_ncu_full.csv",
     "gram_f32_12500000": "r2_gram32_v2_ncu_full.csv",
     "linearize_f64_1048576": "r2_lin_single_ncu_full.csv",
 }
