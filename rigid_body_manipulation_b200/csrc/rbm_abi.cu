@@ -353,12 +353,45 @@ int analyze_model(const char* who, int nj, const double* hposes_Rt, const double
   std::memcpy(g + GP_SENR, pose_sen_Rt ? pose_sen_Rt : ident, 12 * sizeof(double));
   for (int i = 0; i < nj; ++i) {
     double* J = g + GP_HEAD + GJ_STRIDE * i;
-    std::memcpy(J + GJ_HR, hposes_Rt + 12 * (i + 1), 12 * sizeof(double));
-    std::memcpy(J + GJ_S, uscrews + 6 * i, 6 * sizeof(double));
-    const double* ax = uscrews + 6 * i + 3;
-    const double wn = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
-    J[GJ_WN] = wn;
-    for (int k = 0; k < 3; ++k) J[GJ_AXIS + k] = wn > 0.0 ? ax[k] / wn : 0.0;
+    const double* hR = hposes_Rt + 12 * (i + 1);
+    const double* ht = hR + 9;
+    const double* sv = uscrews + 6 * i;
+    const double* sw = sv + 3;
+    std::memcpy(J + GJ_S, sv, 6 * sizeof(double));
+    const double wn = std::sqrt(sw[0] * sw[0] + sw[1] * sw[1] + sw[2] * sw[2]);
+    J[GJ_NW] = -wn;
+    if (wn == 0.0) {  // prismatic: R = hR, p = ht - q v
+      for (int k = 0; k < 9; ++k) J[GJ_RC + k] = hR[k];
+      for (int k = 0; k < 3; ++k) { J[GJ_PC + k] = -sv[k]; J[GJ_PD + k] = ht[k]; }
+    } else {
+      // fold the exponential's constants (layout comment in rbm_model.cuh)
+      const double a[3] = {sw[0] / wn, sw[1] / wn, sw[2] / wn}, r[3] = {sv[0] / wn, sv[1] / wn, sv[2] / wn};
+      auto cross = [](const double* x, const double* y, double* o) {
+        o[0] = x[1] * y[2] - x[2] * y[1]; o[1] = x[2] * y[0] - x[0] * y[2]; o[2] = x[0] * y[1] - x[1] * y[0];
+      };
+      for (int c = 0; c < 3; ++c) {  // column c of hR
+        const double col[3] = {hR[c], hR[3 + c], hR[6 + c]};
+        const double ac = a[0] * col[0] + a[1] * col[1] + a[2] * col[2];
+        double xc[3];
+        cross(a, col, xc);
+        for (int rr = 0; rr < 3; ++rr) {
+          J[GJ_RC + 3 * rr + c] = a[rr] * ac;
+          J[GJ_RA + 3 * rr + c] = col[rr] - a[rr] * ac;
+          J[GJ_RB + 3 * rr + c] = xc[rr];
+        }
+      }
+      const double at = a[0] * ht[0] + a[1] * ht[1] + a[2] * ht[2], ar = a[0] * r[0] + a[1] * r[1] + a[2] * r[2];
+      const double av = a[0] * sv[0] + a[1] * sv[1] + a[2] * sv[2];
+      double axr[3], axt[3];
+      cross(a, r, axr);
+      cross(a, ht, axt);
+      for (int k = 0; k < 3; ++k) {
+        J[GJ_PA + k] = ht[k] - a[k] * at - axr[k];
+        J[GJ_PB + k] = axt[k] + r[k] - ar * a[k];
+        J[GJ_PC + k] = -av * a[k];
+        J[GJ_PD + k] = a[k] * at + axr[k];
+      }
+    }
     std::memcpy(J + GJ_G, simats + 36 * (i + 1), 36 * sizeof(double));
     RigidForm rf;
     J[GJ_RIGID] = rigid_form(simats + 36 * (i + 1), &rf) ? 1.0 : 0.0;

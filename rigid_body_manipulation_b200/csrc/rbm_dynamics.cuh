@@ -94,12 +94,19 @@ struct GenericEval {
   const T* zero;   // 18 zeros: base twist / acceleration / tip wrench switched off
   int nj_;
   RBM_HD int nj() const { return nj_; }
+  // generic_rnea writes tau[0 .. nj): the padding entries of the MAXJ-sized arrays must not carry stack garbage into the masked
+  // dense algebra downstream (0 * NaN)
+  RBM_HD static void clear(T (&tau)[MAXJ]) {
+#pragma unroll
+    for (int k = 0; k < MAXJ; ++k) tau[k] = T(0);
+  }
   RBM_HD static bool is_hinge(int) { return false; }  // generic_rnea evaluates its own trigonometry
   RBM_HD void trig(const T (&)[MAXJ], T (&)[MAXJ], T (&)[MAXJ]) const {}
   RBM_HD static bool q_matters(int) { return true; }
   RBM_HD static bool qd_matters(int) { return true; }
   RBM_HD void id(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qd)[MAXJ], const T (&qdd)[MAXJ],
                                      T (&tau)[MAXJ]) const {
+    clear(tau);
     generic_rnea<T, 0>(sp, sp, nj_, q, qd, qdd, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
   }
   RBM_HD void last_twists(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qd)[MAXJ], const T (&qdd)[MAXJ],
@@ -114,12 +121,14 @@ struct GenericEval {
     for (int k = 0; k < MAXJ; ++k) qdd0[k] = T(0);
     // full base (twist_0, dtwist_0, tip wrench): with a moving base d tau / d qd contains V_0 x (S qd) coupling terms, so the base
     // twist must stay on; the gravity / tip-wrench parts are the same in every evaluation and cancel in the finite differences
+    clear(tau);
     generic_rnea<T, 0>(sp, sp, nj_, q, qd, qdd0, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
   }
   RBM_HD void id_inertia(const T (&q)[MAXJ], const T (&)[MAXJ], const T (&)[MAXJ], const T (&qdd)[MAXJ], T (&tau)[MAXJ]) const {
     T qd0[MAXJ];
 #pragma unroll
     for (int k = 0; k < MAXJ; ++k) qd0[k] = T(0);
+    clear(tau);
     generic_rnea<T, 0>(sp, zero, nj_, q, qd0, qdd, tau, nullptr, nullptr, nullptr, nullptr, nullptr);
   }
   RBM_HD void id_bias(const T (&q)[MAXJ], const T (&c)[MAXJ], const T (&s)[MAXJ], const T (&qd)[MAXJ], T (&tau)[MAXJ]) const {

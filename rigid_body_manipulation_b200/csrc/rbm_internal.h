@@ -73,10 +73,12 @@ class DeviceGuard {
 template <class T> struct ModelView;
 template <> struct ModelView<double> {
   static const double* generic(const rbm_model* m) { return m->d_gp64; }
+  static const double* generic_host(const rbm_model* m) { return m->gp64.data(); }
   static const FastParams<double>& fast(const rbm_model* m) { return m->fp64; }
 };
 template <> struct ModelView<float> {
   static const float* generic(const rbm_model* m) { return m->d_gp32; }
+  static const float* generic_host(const rbm_model* m) { return m->gp32.data(); }
   static const FastParams<float>& fast(const rbm_model* m) { return m->fp32; }
 };
 

@@ -5,6 +5,7 @@
 // re-read: HBM traffic == algorithmic traffic == 24 * sizeof(T) bytes per sample.
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 
 #include "rbm_async.cuh"
 #include "rbm_internal.h"
@@ -151,13 +152,20 @@ __device__ __forceinline__ void stage_params(const T* __restrict__ gp, int count
   __syncthreads();
 }
 
+// NJ > 0: the parameter block is a by-value argument (constant bank), no staging; NJ == 0: run-time joint count, block staged in shared memory
 template <class T, int NJ>
-__global__ void __launch_bounds__(kBlock) k_rnea_generic_soa(const T* __restrict__ gp, int nj, int nparams, const T* __restrict__ q,
-                                                             const T* __restrict__ qd, const T* __restrict__ qdd, T* __restrict__ tau,
-                                                             T* __restrict__ Vout, T* __restrict__ dVout, int64_t n, int64_t ld) {
+__global__ void __launch_bounds__(kBlock) k_rnea_generic_soa(const __grid_constant__ GenericBlock<T, (NJ > 0 ? NJ : 1)> P, const T* __restrict__ gp, int nj,
+                                                             int nparams, const T* __restrict__ q, const T* __restrict__ qd, const T* __restrict__ qdd,
+                                                             T* __restrict__ tau, T* __restrict__ Vout, T* __restrict__ dVout, int64_t n, int64_t ld) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sp = reinterpret_cast<T*>(smem_raw);
-  stage_params(gp, nparams, sp);
+  const T* sp;
+  if constexpr (NJ > 0) {
+    sp = P.v;
+  } else {
+    T* staged = reinterpret_cast<T*>(smem_raw);
+    stage_params(gp, nparams, staged);
+    sp = staged;
+  }
   const int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (s >= n) return;
   constexpr int MAXJ = NJ > 0 ? NJ : RBM_MAX_JOINTS;
@@ -400,8 +408,13 @@ int launch_rnea_soa(const rbm_model* m, const T* q, const T* qd, const T* qdd, T
   } else {
     const int np = generic_param_count(m->nj);
     const size_t sm = sizeof(T) * np;
-    if (m->nj == 6) k_rnea_generic_soa<T, 6><<<grid, kBlock, sm, st>>>(ModelView<T>::generic(m), m->nj, np, q, qd, qdd, tau, V, dV, n, ld);
-    else k_rnea_generic_soa<T, 0><<<grid, kBlock, sm, st>>>(ModelView<T>::generic(m), m->nj, np, q, qd, qdd, tau, V, dV, n, ld);
+    if (m->nj == 6) {
+      GenericBlock<T, 6> P;
+      std::memcpy(P.v, ModelView<T>::generic_host(m), sizeof(P.v));
+      k_rnea_generic_soa<T, 6><<<grid, kBlock, 0, st>>>(P, nullptr, 6, np, q, qd, qdd, tau, V, dV, n, ld);
+    } else {
+      k_rnea_generic_soa<T, 0><<<grid, kBlock, sm, st>>>(GenericBlock<T, 1>{}, ModelView<T>::generic(m), m->nj, np, q, qd, qdd, tau, V, dV, n, ld);
+    }
   }
   RBM_CUDA_TRY(cudaGetLastError());
   return RBM_OK;

@@ -281,54 +281,29 @@ template <class T> RBM_HD G3<T> matT_vec(const T* R, G3<T> v) {
 
 template <class T> RBM_HD T abs_t(T x) { return x < T(0) ? -x : x; }
 
-// T_i = SE3.exp(-S q) . M_i  (dynamics.py:126) with liegroups' Rodrigues / left-Jacobian formulas and
-// its isclose(angle, 0) first-order branch (atol 1e-8).  Writes R (row-major 9) and p (3).
+// T_i = SE3.exp(-S q) . M_i  (dynamics.py:126).  The exponential (liegroups' Rodrigues / left-Jacobian formulas) and the product with
+// the home pose are folded at model creation into R = c RA + s RB + RC, p = c PA + s PB + q PC + PD (rbm_model.cuh): 27 FMAs and one
+// sincos per revolute joint, no division, no composition at run time; a prismatic joint costs 3 FMAs.  The branch on the joint kind
+// depends on the model only (warp-uniform; a constant-bank compare in the unrolled kernel).
 template <class T>
-RBM_HD void joint_transform(const T* J /* per-joint param block */, T q, T* R, T* p) {
-  const T* hR = J + GJ_HR;
-  G3<T> ht = g3(J + GJ_HT);
-  G3<T> rho = (-q) * g3(J + GJ_S);
-  G3<T> ax = g3(J + GJ_AXIS);
-  const T wn = J[GJ_WN];
-  if (wn == T(0)) {
-    // pure translation (every sample of a batch takes this branch together: it depends on the model only).  liegroups reaches the same
-    // numbers through its small-angle branch: R = (I + [0]x) M_R, t = rho + 0.5 * 0 x rho.
+RBM_HD void joint_trig(const T* J /* per-joint param block */, T q, T& s, T& c) {
+  const T nw = J[GJ_NW];
+  if (nw == T(0)) { s = T(0); c = T(1); return; }
+  sincos_t(q * nw, &s, &c);
+}
+template <class T>
+RBM_HD void joint_pose(const T* J, T q, T s, T c, T* R, T* p) {
+  if (J[GJ_NW] == T(0)) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) R[k] = hR[k];
-    p[0] = ht.x + rho.x; p[1] = ht.y + rho.y; p[2] = ht.z + rho.z;
+    for (int k = 0; k < 9; ++k) R[k] = J[GJ_RC + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = J[GJ_PD + k] + q * J[GJ_PC + k];
     return;
   }
-  const T theta = -q * wn;   // signed rotation angle about `ax`
-  T E[9], te[3];
-  if (abs_t(theta) <= T(1e-8)) {
-    // R = I + [phi]x ,  J_l = I + 0.5 [phi]x   with phi = -S_w q
-    G3<T> phi = (-q) * g3(J + GJ_S + 3);
-    E[0] = T(1); E[1] = -phi.z; E[2] = phi.y;
-    E[3] = phi.z; E[4] = T(1); E[5] = -phi.x;
-    E[6] = -phi.y; E[7] = phi.x; E[8] = T(1);
-    G3<T> t = rho + T(0.5) * gcross(phi, rho);
-    te[0] = t.x; te[1] = t.y; te[2] = t.z;
-  } else {
-    T s, c;
-    sincos_t(theta, &s, &c);
-    const T oc = T(1) - c;
-    E[0] = c + oc * ax.x * ax.x;        E[1] = oc * ax.x * ax.y - s * ax.z; E[2] = oc * ax.x * ax.z + s * ax.y;
-    E[3] = oc * ax.y * ax.x + s * ax.z; E[4] = c + oc * ax.y * ax.y;        E[5] = oc * ax.y * ax.z - s * ax.x;
-    E[6] = oc * ax.z * ax.x - s * ax.y; E[7] = oc * ax.z * ax.y + s * ax.x; E[8] = c + oc * ax.z * ax.z;
-    // J_l rho = (s/th) rho + (1 - s/th) a (a.rho) + ((1-c)/th) a x rho
-    const T sa = s / theta, ob = oc / theta;
-    const T ar = ax.x * rho.x + ax.y * rho.y + ax.z * rho.z;
-    G3<T> t = sa * rho + ((T(1) - sa) * ar) * ax + ob * gcross(ax, rho);
-    te[0] = t.x; te[1] = t.y; te[2] = t.z;
-  }
-  // R = E hR ; p = E ht + te
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
+  for (int k = 0; k < 9; ++k) R[k] = J[GJ_RC + k] + c * J[GJ_RA + k] + s * J[GJ_RB + k];
 #pragma unroll
-    for (int cc = 0; cc < 3; ++cc) R[3 * r + cc] = E[3 * r] * hR[cc] + E[3 * r + 1] * hR[3 + cc] + E[3 * r + 2] * hR[6 + cc];
-  }
-  G3<T> pp = mat_vec(E, ht);
-  p[0] = pp.x + te[0]; p[1] = pp.y + te[1]; p[2] = pp.z + te[2];
+  for (int k = 0; k < 3; ++k) p[k] = J[GJ_PD + k] + q * J[GJ_PC + k] + c * J[GJ_PA + k] + s * J[GJ_PB + k];
 }
 
 // Ad(T) [v; w] = [R v + p x (R w); R w]
@@ -344,10 +319,11 @@ RBM_HD void adjointT_apply(const T* R, G3<T> p, G3<T> f, G3<T> m, G3<T>& fo, G3<
   mo = matT_vec(R, m - gcross(p, f));
 }
 
-// Generic RNEA for one sample.  NJ > 0: compile-time joint count (loops unroll, state in registers);
-// NJ == 0: run-time count (per-link state lives in local memory).  The body wrench
-// b_i = G_i dV_i - ad(V_i)^T G_i V_i is formed during the forward sweep so that only (R_i, p_i, b_i)
-// survive until the backward sweep.  Optional full-state outputs mirror the reference's return value
+// Generic RNEA for one sample.  NJ > 0: compile-time joint count (loops unroll, state in registers, `sp` may be a constant-bank
+// kernel argument so every model constant is an FMA operand); NJ == 0: run-time count (per-link state lives in local memory).
+// The body wrench b_i = G_i dV_i - ad(V_i)^T G_i V_i is formed during the forward sweep; of the link transforms only (sin, cos) of the
+// joint are kept -- the backward sweep re-forms (R_i, p_i) from them (27 FMAs) instead of holding 12 numbers per link live, which is
+// what made the unrolled fp64 kernel spill at 254 registers.  Optional full-state outputs mirror the reference's return value
 // (tau, poses, twists, dtwists) for the scalar drop-in API.
 template <class T, int NJ>
 RBM_HD void generic_rnea(const T* __restrict__ sp, const T* __restrict__ base /* [V0 | dV0 | Ftip], normally == sp */, int nj_rt, const T* q, const T* qd, const T* qdd, T* tau,
@@ -355,8 +331,7 @@ RBM_HD void generic_rnea(const T* __restrict__ sp, const T* __restrict__ base /*
                                              T* Vlast /* [6] or null */, T* dVlast /* [6] or null */) {
   constexpr int MAXJ = NJ > 0 ? NJ : RBM_MAX_JOINTS;
   const int nj = NJ > 0 ? NJ : nj_rt;
-  T Rs[MAXJ + 1][9];
-  T ps[MAXJ + 1][3];
+  T sn[MAXJ], cs[MAXJ];
   T bs[MAXJ][6];
   G3<T> v = g3(base + GP_V0), w = g3(base + GP_V0 + 3);
   G3<T> a = g3(base + GP_DV0), l = g3(base + GP_DV0 + 3);
@@ -367,12 +342,14 @@ RBM_HD void generic_rnea(const T* __restrict__ sp, const T* __restrict__ base /*
 #pragma unroll
   for (int i = 0; i < nj; ++i) {
     const T* J = sp + GP_HEAD + GJ_STRIDE * i;
-    joint_transform(J, q[i], Rs[i], ps[i]);
-    G3<T> p = g3(ps[i]);
+    T R[9], pp[3];
+    joint_trig(J, q[i], sn[i], cs[i]);
+    joint_pose(J, q[i], sn[i], cs[i], R, pp);
+    G3<T> p = g3(pp);
     G3<T> sv = g3(J + GJ_S), sw = g3(J + GJ_S + 3);
     G3<T> vn, wn, an, ln;
-    adjoint_apply(Rs[i], p, v, w, vn, wn);
-    adjoint_apply(Rs[i], p, a, l, an, ln);
+    adjoint_apply(R, p, v, w, vn, wn);
+    adjoint_apply(R, p, a, l, an, ln);
     v = vn + qd[i] * sv;  // Eq. 8.51
     w = wn + qd[i] * sw;
     // Eq. 8.52: ad(V) S = [w x s_v + v x s_w ; w x s_w]
@@ -382,8 +359,8 @@ RBM_HD void generic_rnea(const T* __restrict__ sp, const T* __restrict__ base /*
     const T dV6[6] = {a.x, a.y, a.z, l.x, l.y, l.z};
     if (poses) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) poses[12 * i + k] = Rs[i][k];
-      poses[12 * i + 9] = ps[i][0]; poses[12 * i + 10] = ps[i][1]; poses[12 * i + 11] = ps[i][2];
+      for (int k = 0; k < 9; ++k) poses[12 * i + k] = R[k];
+      poses[12 * i + 9] = pp[0]; poses[12 * i + 10] = pp[1]; poses[12 * i + 11] = pp[2];
     }
     if (twists) {
 #pragma unroll
@@ -423,16 +400,18 @@ RBM_HD void generic_rnea(const T* __restrict__ sp, const T* __restrict__ base /*
     dVlast[0] = a.x; dVlast[1] = a.y; dVlast[2] = a.z; dVlast[3] = l.x; dVlast[4] = l.y; dVlast[5] = l.z;
   }
   if (!tau) return;
-  // tip transform and wrench (dynamics.py:136-137)
-#pragma unroll
-  for (int k = 0; k < 9; ++k) Rs[nj][k] = sp[GP_TIPR + k];
-  ps[nj][0] = sp[GP_TIPT]; ps[nj][1] = sp[GP_TIPT + 1]; ps[nj][2] = sp[GP_TIPT + 2];
   G3<T> f = g3(base + GP_FTIP), m = g3(base + GP_FTIP + 3);
 #pragma unroll
   for (int i = nj - 1; i >= 0; --i) {
     const T* J = sp + GP_HEAD + GJ_STRIDE * i;
     G3<T> fo, mo;
-    adjointT_apply(Rs[i + 1], g3(ps[i + 1]), f, m, fo, mo);   // Eq. 8.53
+    if (i == nj - 1) {  // tip transform (dynamics.py:136-137)
+      adjointT_apply(sp + GP_TIPR, g3(sp + GP_TIPT), f, m, fo, mo);
+    } else {  // T_{i+1} again, from the joint's (sin, cos)
+      T R[9], pp[3];
+      joint_pose(J + GJ_STRIDE, q[i + 1], sn[i + 1], cs[i + 1], R, pp);
+      adjointT_apply(R, g3(pp), f, m, fo, mo);   // Eq. 8.53
+    }
     f = fo + g3(bs[i]);
     m = mo + g3(bs[i] + 3);
     tau[i] = f.x * J[GJ_S] + f.y * J[GJ_S + 1] + f.z * J[GJ_S + 2] + m.x * J[GJ_S + 3] + m.y * J[GJ_S + 4] + m.z * J[GJ_S + 5];  // Eq. 8.54

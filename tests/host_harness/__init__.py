@@ -91,12 +91,19 @@ def sensor_regressor(pose_Rt, V, dV):
     return Vs, dVs, Y
 
 
+def _lib_main():
+    from rigid_body_manipulation_b200 import _lib as rbm_lib
+
+    return rbm_lib.load()
+
+
 def _model_args(analysis):
     """analysis = engine.analyze_model(...) = (path name, fast params, generic params) -> ctypes-ready (path id, fp, gp, nj)."""
     path, fast, generic = analysis
     fp = np.ascontiguousarray(fast, dtype=np.float64)
     gp = np.ascontiguousarray(generic, dtype=np.float64)
-    return C.c_int(PATH_ID[path]), fp, gp, C.c_int((len(gp) - 42) // 59)
+    nj = next(k for k in range(1, 17) if _lib_main().rbm_generic_param_count(k) == len(gp))  # the block's size names the joint count
+    return C.c_int(PATH_ID[path]), fp, gp, C.c_int(nj)
 
 
 def linearize(analysis, q, qd, u=None, dt=0.002, eps=1e-8, centered=True):

@@ -40,7 +40,7 @@ def test_model_analysis_selects_the_specialised_path_for_the_reference_robot(t):
     assert np.allclose(fast[27:27 + 30].reshape(5, 6)[:, :3], 0.05333333) and not fast[27:27 + 30].reshape(5, 6)[:, 3:].any()
     assert fast[-1] == 1.0 and np.array_equal(fast[-13:-4].reshape(3, 3), np.diag([-1.0, -1.0, 1.0]))  # Rz(180 deg) sensor site, snapped
     assert analyze(g, force_generic=True)[0] == "generic"
-    assert len(generic) == 42 + 59 * 6 and np.array_equal(generic[6:12], g["dtwist_0"])
+    assert len(generic) == 42 + 83 * 6 and np.array_equal(generic[6:12], g["dtwist_0"])  # GP_HEAD + GJ_STRIDE * nj (csrc/rbm_model.cuh)
 
 
 def test_model_analysis_fallbacks():

@@ -75,6 +75,8 @@ def main():
     ap.add_argument("--generic", action="store_true", help="force the generic (any-model) kernel")
     ap.add_argument("--min-exp", type=int, default=4)
     ap.add_argument("--dtypes", default="f32,f64")
+    ap.add_argument("--model", default="hammer", help="hammer (the reference robot) or nj6: the structure-free 6-joint model of "
+                    "tests/golden/ref_inverse_generic_nj6.npz (dense inertias, general screws, moving base, tip wrench)")
     args = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -82,8 +84,12 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     from rigid_body_manipulation_b200 import distributed as rbm_dist
 
-    c = rbm_model.load_packaged("sequential", "hammer")
-    m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, force_generic=args.generic, device=local)
+    if args.model == "nj6":
+        g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ref_inverse_generic_nj6.npz"))
+        m = Model(g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"], wrench_tip=g["wrench_tip"], pose_tip_ee=g["pose_tip"], device=local)
+    else:
+        c = rbm_model.load_packaged("sequential", "hammer")
+        m = Model(c.hposes_Rt, c.simats, c.uscrews, c.twist_0, c.dtwist_0, force_generic=args.generic, device=local)
     free_b = torch.cuda.mem_get_info()[0]
     lines = []
     for name, dt, es in (("f32", torch.float32, 4), ("f64", torch.float64, 8)):
@@ -118,7 +124,7 @@ def main():
 
             pms = timed(pstep)
             gbs = 24 * es * B_total / (ms * 1e-3) / 1e9  # aggregate over all ranks
-            lines.append({"kernel_path": m.kernel_path, "dtype": name, "n_gpus": WORLD, "B": B_total, "B_per_gpu": B, "ms": ms, "samples_per_s": B_total / (ms * 1e-3),
+            lines.append({"model": args.model, "kernel_path": m.kernel_path, "dtype": name, "n_gpus": WORLD, "B": B_total, "B_per_gpu": B, "ms": ms, "samples_per_s": B_total / (ms * 1e-3),
                           "GBps_algorithmic": gbs, "frac_of_measured_hbm": gbs / PEAK / WORLD,
                           "buffer_sets": nset, "planned_ms": pms, "planned_samples_per_s": B_total / (pms * 1e-3),
                           "planned_GBps_algorithmic": 6 * es * B_total / (pms * 1e-3) / 1e9})
