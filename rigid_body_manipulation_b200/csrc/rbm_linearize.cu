@@ -30,9 +30,14 @@ constexpr int kLinBlock = 128;
 // Round 2: a lane-PAIR version (two lanes share a state: +eps / -eps evaluations, half the M^-1 rows each, 168 or 128 registers, 12 or 16
 // warps per SM) was built, passed the parity suite and LOST: 2.10 / 2.14 against 2.80 G states/s (ncu: +17 % instructions, +14 % DRAM
 // write traffic from half-warp stores, FP64 pipe 46 % instead of 55 %).  Kept as experiments/k_linearize_pair.cu.inc.
+// Also round 2: a persistent variant (one two-stage TMA pipeline of 32-state input sub-tiles per warp, no CTA barrier) LOST 9 %
+// (2.76 against 3.03; persistent with plain loads 2.69): the hardware block scheduler's dynamic placement beats a static tile loop
+// here.  What did help is an L2 prefetch of a later block's 18 input rows: +2 ... 3 % at a distance of 64 ... 148 blocks (3.06 at 64,
+// 3.04 at 100 / 148, 3.00 at 200 / 296, 2.97 without; kbench, 200 launches).
 #ifndef RBM_LIN_MINB
 #define RBM_LIN_MINB 2
 #endif
+constexpr int kLinPrefetchBlocks = 64;
 
 // evaluators, Cholesky solve, linearize_state, forward_dynamics_state, closed_loop_env: rbm_dynamics.cuh (shared with the host harness)
 
@@ -69,6 +74,17 @@ __global__ void __launch_bounds__(kLinBlock, RBM_LIN_MINB) k_linearize_fast(cons
                                                               T* __restrict__ qdd_out, int64_t n, int64_t ld) {
   const int64_t s = (int64_t)blockIdx.x * kLinBlock + threadIdx.x;
   if (s >= n) return;
+  // One state is ~6 000 instructions behind 18 loads and two warps per scheduler cannot cover their DRAM latency (15 % of the stall
+  // samples sat on the first use of q): pull the inputs of the block that starts kLinPrefetchBlocks later into L2 now.
+  constexpr int64_t ahead = (int64_t)kLinPrefetchBlocks * kLinBlock;
+  if (s + ahead < n) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q + k * ld + s + ahead));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(qd + k * ld + s + ahead));
+      if (u) asm volatile("prefetch.global.L2 [%0];" ::"l"(u + k * ld + s + ahead));
+    }
+  }
   FastEval<T, D> ev{P};
   linearize_state<T>(ev, q, qd, u, dt, eps, centered != 0, A, B, qdd_out, s, ld);
 }
