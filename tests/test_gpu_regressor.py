@@ -69,12 +69,13 @@ def _gram_reference(g, traj, f):
 
 
 @pytest.mark.parametrize("fname", ["ref_inverse_hammer.npz", "ref_inverse_generic_nj6.npz", "ref_inverse_generic_nj9.npz"])
-@pytest.mark.parametrize("n", [1, 255, 4096, 100_003, 100_352, 300_002])
+@pytest.mark.parametrize("n", [1, 255, 766, 1_026, 4096, 100_003, 100_352, 300_002])
 @pytest.mark.parametrize("no_tma", [False, True])
 def test_gram_matches_materialised_normal_equations(fname, n, no_tma):
-    """Aligned batches of >= 256 samples on the fast path take the TMA-pipelined kernel (4096, 100_352, and 300_002 with its
-    ragged 226-sample tail); odd n (row pitch not 16-byte aligned), tiny n, generic models and no_tma=True take the direct-load
-    kernel.  Both must agree with the materialised normal equations."""
+    """Aligned batches of >= 512 samples on the fast path take the TMA-pipelined kernel (512-sample tiles, two samples per thread:
+    4096 and 100_352 are whole tiles; 766 has one tile + a 254-sample tail (first half-tile only), 1_026 two tiles + 2 samples,
+    300_002 a 482-sample tail (both half-tiles)); odd n (row pitch not 16-byte aligned), tiny n, generic models and no_tma=True take
+    the direct-load kernel.  Both must agree with the materialised normal equations."""
     g = load_golden(fname)
     m = model_from_golden(g, no_tma=no_tma)
     nj = m.nj
