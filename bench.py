@@ -257,6 +257,7 @@ class GramWorkload:
     metric, unit = "regressor_gram_samples_per_s", "samples/s"
     launches_per_step = 2  # accumulate + finalize
     name = "gram"
+    graphable = False  # 0.2-0.4 ms steps (and a collective at N > 1): the host is far from the critical path
 
     def __init__(self, args, model, rank, torch, dtype=None, samples=None, host_buffers=True):
         from rigid_body_manipulation_b200 import distributed
@@ -336,6 +337,7 @@ class LinearizeWorkload:
     metric, unit = "lqr_linearizations_per_s", "states/s"
     launches_per_step = 1
     name = "linearize"
+    graphable = False  # 0.35 ms steps
 
     def __init__(self, args, model, rank, torch, dtype=None, samples=None, host_buffers=True):
         self.torch, self.model, self.B = torch, model, samples or args.samples
@@ -403,14 +405,35 @@ class Timer:
         (est,) = self.max_over_ranks([(time.perf_counter() - t0) / 3])
         return int(min(20000, max(10, seconds / max(est, 1e-6))))
 
-    def timed(self, step, steps):
-        """total ms for exactly `steps` back-to-back steps (max over ranks)"""
+    def capture(self, step, steps):
+        """CUDA graph of `steps` back-to-back steps (the library launches on torch's current stream, so its launches -- programmatic
+        dependent launch attributes included -- are captured as issued), or None when the capture fails.  A 2^20-sample launch lasts
+        ~30 us and one call through Python + ctypes costs ~14 us of host time (tools/bench_launch_overhead.py): on a busy host an eager
+        loop starves the GPU; replaying a graph takes the host out of the timed region."""
+        torch = self.torch
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(steps):
+                    step()
+            g.replay()  # one untimed replay
+            torch.cuda.synchronize()
+            return g
+        except Exception:  # pragma: no cover - depends on the driver
+            torch.cuda.synchronize()
+            return None
+
+    def timed(self, step, steps, graph=None):
+        """total ms for exactly `steps` back-to-back steps (max over ranks); `graph` = those steps captured by capture()"""
         torch = self.torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
         e0.record()
-        for _ in range(steps):
-            step()
+        if graph is not None:
+            graph.replay()
+        else:
+            for _ in range(steps):
+                step()
         e1.record()
         self.barrier()
         return self.max_over_ranks([e0.elapsed_time(e1)])[0]
@@ -549,6 +572,34 @@ def small_extra(cls, args, model, rank, world, torch, tm, dtype, samples):
     return out
 
 
+def generic_extra(args, rank, world, local, torch, tm):
+    """The any-model kernel on a model with NO structure (tests/golden/ref_inverse_generic_nj6.npz: general screws, dense SPD inertias,
+    moving base, tip wrench).  It is bound by the FP64 pipe, not by HBM: 1680 FP64 instructions per sample (ncu,
+    profiles/r2_generic_nj6_ncu_full.csv) against 64 FP64 lanes per SM and clock."""
+    from rigid_body_manipulation_b200.engine import Model
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "ref_inverse_generic_nj6.npz")
+    if not os.path.exists(path):
+        return {"skipped": "tests/golden/ref_inverse_generic_nj6.npz not found"}
+    g = np.load(path)
+    gm = Model(g["hposes_Rt"], g["simats"], g["uscrews"], g["twist_0"], g["dtwist_0"], wrench_tip=g["wrench_tip"], pose_tip_ee=g["pose_tip"], device=local)
+    out = {}
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    for dtype in ("f64", "f32"):
+        r = small_extra(RneaWorkload, args, gm, rank, world, torch, tm, dtype, 1 << 22)
+        r["workload"] = f"batched inverse dynamics, generic kernel, structure-free 6-joint model, {1 << 22} samples, {dtype}"
+        r["kernel_path"] = gm.kernel_path
+        if dtype == "f64":
+            ceiling = sms * 64 * 1.965e9 / 1680.0  # samples/s per GPU at 100 % FP64-pipe utilisation and the maximum SM clock
+            r["bound"] = "fp64 pipe"
+            r["fp64_instructions_per_sample"] = 1680
+            r["fp64_ceiling_samples_per_s"] = world * ceiling
+            r["frac_of_fp64_ceiling"] = r["value"] / (world * ceiling)
+        out[dtype] = r
+    del gm
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -585,11 +636,18 @@ def run_gpu_arm(args):
     tm.barrier()
     n_heat = tm.heat_count(wl.step, 0.3)  # ~0.3 s of untimed steps so that the clock sampler sees loaded clocks
     tm.barrier()
+    # the K timed steps as one CUDA graph (workloads whose step contains a collective stay eager); every rank decides alike
+    graph = None
+    if not args.eager and getattr(wl, "graphable", True):
+        graph = tm.capture(wl.step, args.steps)
+        (ok,) = tm.max_over_ranks([0.0 if graph is not None else 1.0])
+        if ok != 0.0:
+            graph = None
     with ClockSampler(local) as clk:
         for _ in range(n_heat):
             wl.step()
         # pass 1 -- the reported value: exactly K steps back to back, bracketed by barrier + synchronize
-        total_ms = tm.timed(wl.step, args.steps)
+        total_ms = tm.timed(wl.step, args.steps, graph=graph)
         # pass 2 -- per-launch durations (an event pair around every launch, same stream)
         kern_ms_isolated = tm.isolated(wl.step, args.steps)
     # one step == one launch of the dominant kernel (plus, for the Gram workload, a single-CTA finalisation): its average
@@ -622,6 +680,7 @@ def run_gpu_arm(args):
                          "f32": gram_extra(args, model, rank, world, local, torch, dist, tm, "f32")}
         extra["linearize"] = small_extra(LinearizeWorkload, args, model, rank, world, torch, tm, "f64", 1 << 20)
         extra["rnea_f32"] = small_extra(RneaWorkload, args, model, rank, world, torch, tm, "f32", 1 << 24)
+        extra["rnea_generic"] = generic_extra(args, rank, world, local, torch, tm)
 
     if rank == 0:
         line = {
@@ -634,6 +693,8 @@ def run_gpu_arm(args):
                        "parallelism": (f"samples sharded x{world}, no collective on this workload" if args.workload != "gram" or world == 1
                                        else f"samples sharded x{world}, one 112-double NCCL all-reduce per step")
                        + ("; extra.gram: configs[2] share per rank with the NCCL all-reduce inside the timed step" if extra else ""),
+                       "launch_mode": (f"CUDA graph of the {args.steps} timed steps, replayed once inside the timed region" if graph is not None
+                                       else "eager: one library call per step from the Python loop"),
                        "numa": numa_all},
             "roofline": roofline_block(wl, kern_ms_avg, kern_ms_isolated, traffic_entry(f"{args.workload}_{wl.dtype}_{B}")),
             "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h, "api": wl.e2e_api, "steps": e2e_steps,
@@ -672,6 +733,7 @@ def main():
     ap.add_argument("--samples", type=int, default=1 << 20, help="samples (states) per GPU per step")
     ap.add_argument("--cpu-samples", type=int, default=0, help="CPU baseline sample count (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--eager", action="store_true", help="time an eager Python loop of library calls instead of replaying a CUDA graph of the K steps")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra.* legs (configs[2] Gram + all-reduce, configs[3] linearisation, fp32 RNEA)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the GPU's NUMA node")
     ap.add_argument("--gram-samples", type=int, default=12_500_000, help="samples per GPU of the extra.gram leg (12.5 M x 8 GPUs = configs[2]'s 100 M)")

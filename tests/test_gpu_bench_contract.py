@@ -28,6 +28,8 @@ def check_common(d):
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert d["value"] > 0 and d["ms_per_step"] > 0
     assert isinstance(d["config"], dict) and "workload" in d["config"] and "model" not in d["config"]
+    if d.get("impl") != "reference":
+        assert d["config"]["launch_mode"].startswith(("CUDA graph", "eager"))
     e = d["e2e"]
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e) and e["value"] > 0
 
@@ -52,6 +54,9 @@ def test_default_workload_line():
         gx = x["gram"][dt_]
         assert gx["samples_per_gpu"] == 300_000 and gx["value"] > 0 and gx["pack_n_ok"] is True and 0 < gx["frac"] < 2
     assert x["linearize"]["value"] > 0 and x["rnea_f32"]["value"] > 0
+    gen = x["rnea_generic"]
+    assert gen["f64"]["kernel_path"] == "generic" and gen["f64"]["value"] > 0 and gen["f32"]["value"] > 0
+    assert gen["f64"]["bound"] == "fp64 pipe" and 0 < gen["f64"]["frac_of_fp64_ceiling"] < 1
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
     k = d["clocks"]
