@@ -413,7 +413,8 @@ class Timer:
         torch = self.torch
         try:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: NCCL's watchdog thread polls events while this thread captures (multi-rank runs)
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 for _ in range(steps):
                     step()
             g.replay()  # one untimed replay
