@@ -113,3 +113,30 @@ def test_generic_recursion_matches_reference_golden(fname):
     Vs, dVs, Y = host_harness.sensor_regressor(g["pose_sen_llj"], out["V"], out["dV"])
     assert rel_err(Vs, g["twist_sen"]).max() < 1e-12 and rel_err(dVs, g["dtwist_sen"]).max() < 1e-12
     assert rel_err(Y, g["regressor"]).max() < 1e-12
+
+
+def test_folded_joint_transform_with_non_unit_screws_and_tiny_angles():
+    """The generic kernel folds SE3.exp(-S q) . M at model creation into R = c RA + s RB + RC, p = c PA + s PB + q PC + PD
+    (csrc/rbm_model.cuh) and has no small-angle branch.  Screws the goldens do not contain -- rotation parts of norm 0.7, 1.9 and 1e-3
+    (nearly prismatic), a rescaled pitch -- and states on both sides of liegroups' isclose(angle, 0) switch (|q| = 1e-9, 2e-8) and far
+    outside the trigonometric fast range (q = 50) must still agree with the vectorised restatement of the reference
+    (dynamics.py:109-157 on liegroups' exp / left Jacobian)."""
+    from oracle import rnea_vec as rv
+
+    g = load_golden("ref_inverse_generic_nj6.npz")
+    us = g["uscrews"].copy()
+    us[0, 3:] *= 0.7
+    us[2, 3:] *= 1.9
+    us[2, :3] *= 0.4
+    us[3, 3:] *= 1e-3
+    traj = g["traj"].copy()
+    traj[2, 0, :] = 1e-9
+    traj[3, 0, :] = -2e-8
+    traj[4, 0, :] = 50.0
+    _, _, gp = engine.analyze_model(g["hposes_Rt"], g["simats"], us, g["twist_0"], g["dtwist_0"], wrench_tip=g["wrench_tip"], pose_tip_ee=g["pose_tip"],
+                                    force_generic=True)
+    out = host_harness.generic_rnea(gp, 6, traj, full=True)
+    ref = rv.inverse_batched(traj, g["hposes_Rt"], g["simats"], us, g["twist_0"], g["dtwist_0"], wrench_tip=g["wrench_tip"], pose_tip_Rt=g["pose_tip"])
+    assert rel_err(out["tau"], ref["tau"]).max() < 1e-12
+    assert np.abs(out["poses"] - ref["poses"]).max() < 1e-12
+    assert rel_err(out["twists"], ref["twists"]).max() < 1e-12 and rel_err(out["dtwists"], ref["dtwists"]).max() < 1e-12
