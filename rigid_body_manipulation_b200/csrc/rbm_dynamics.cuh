@@ -154,6 +154,16 @@ struct GenericEval {
 };
 
 // ---- dense SPD solve (Cholesky, in place in the lower triangle; the diagonal holds 1 / L_ii) ------------
+// 1 / sqrt(x): the device's rsqrt is one short sequence instead of a square root followed by a division, and it sits on the serial
+// chain of the factorisation (results within 1 ulp of the two-step form; the host build of the harness uses the two-step form)
+template <class T>
+RBM_HD T inv_sqrt(T x) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(x);
+#else
+  return T(1) / std::sqrt(x);
+#endif
+}
 template <class T, int MAXJ>
 RBM_HD void cholesky(T (&M)[MAXJ][MAXJ], int n) {
 #pragma unroll
@@ -162,7 +172,7 @@ RBM_HD void cholesky(T (&M)[MAXJ][MAXJ], int n) {
       T d = M[j][j];
 #pragma unroll
       for (int k = 0; k < j; ++k) d -= M[j][k] * M[j][k];
-      const T inv = T(1) / sqrt(d);
+      const T inv = inv_sqrt(d);
       M[j][j] = inv;
 #pragma unroll
       for (int i = j + 1; i < MAXJ; ++i) {
