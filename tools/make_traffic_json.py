@@ -12,7 +12,7 @@ SOURCES = {
     "rnea_f32_1048576": "r1c_rnea_f32_ncu_full.csv",
     "gram_f64_12500000": "r2_gram_v3_ncu_full.csv",
     "gram_f32_12500000": "r2_gram32_v3_ncu_full.csv",
-    "linearize_f64_1048576": "r2_lin_single_ncu_full.csv",
+    "linearize_f64_1048576": "r2_lin_final_ncu_full.csv",
 }
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
