@@ -322,3 +322,37 @@ def test_full_size_properties_of_configs1():
     assert rel_err(m.rnea_aos(dev).cpu().numpy(), t1.t().cpu().numpy()).max() < 1e-13
     host = m.rnea_host_soa(*(np.ascontiguousarray(traj[:, k, :].T) for k in range(3)))
     assert np.array_equal(host, t1.cpu().numpy())                       # same kernel behind the host entry
+
+
+def test_generic_kernel_with_non_unit_screws_and_tiny_angles():
+    """The generic kernels fold SE3.exp(-S q) . M into affine forms of (cos, sin, q) at model creation and carry no small-angle branch
+    (csrc/rbm_model.cuh).  Screws outside the goldens -- rotation parts of norm 0.7, 1.9 and 1e-3, a rescaled pitch -- and states on both
+    sides of liegroups' isclose(angle, 0) switch and far outside the trigonometric fast range, through the unrolled constant-bank kernel
+    (SoA, nj = 6) and the run-time-loop kernel (AoS / full state), against the vectorised restatement of dynamics.py:109-157."""
+    from rigid_body_manipulation_b200.engine import Model
+
+    g = load_golden("ref_inverse_generic_nj6.npz")
+    us = g["uscrews"].copy()
+    us[0, 3:] *= 0.7
+    us[2, 3:] *= 1.9
+    us[2, :3] *= 0.4
+    us[3, 3:] *= 1e-3
+    rng = np.random.default_rng(11)
+    n = 1000
+    traj = np.stack([rng.uniform(-3, 3, (n, 6)), rng.standard_normal((n, 6)), rng.standard_normal((n, 6)) * 3], axis=1)
+    traj[0] = 0.0
+    traj[1, 0, :] = 1e-9
+    traj[2, 0, :] = -2e-8
+    traj[3, 0, :] = 50.0
+    traj[4, 0, :] = -2.0e5  # beyond the fast range of the trigonometry
+    m = Model(g["hposes_Rt"], g["simats"], us, g["twist_0"], g["dtwist_0"], wrench_tip=g["wrench_tip"], pose_tip_ee=g["pose_tip"], device=0)
+    assert m.kernel_path == "generic"
+    ref = rv.inverse_batched(traj, g["hposes_Rt"], g["simats"], us, g["twist_0"], g["dtwist_0"], wrench_tip=g["wrench_tip"], pose_tip_Rt=g["pose_tip"])
+    q, qd, qdd = soa(traj)
+    tau, V, dV = m.rnea(q, qd, qdd, want_twists=True)
+    assert rel_err(tau.t().cpu().numpy(), ref["tau"]).max() < TOL64
+    assert rel_err(V.t().cpu().numpy(), ref["twists"][:, 6]).max() < TOL64 and rel_err(dV.t().cpu().numpy(), ref["dtwists"][:, 6]).max() < TOL64
+    full = m.rnea_full(torch.as_tensor(traj, device="cuda"))
+    assert rel_err(full[0].cpu().numpy(), ref["tau"]).max() < TOL64
+    assert np.abs(full[1].cpu().numpy() - ref["poses"]).max() < 1e-9
+    assert rel_err(m.rnea(q.float(), qd.float(), qdd.float()).t().cpu().numpy()[:4], ref["tau"][:4]).max() < 1e-3
