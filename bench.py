@@ -421,7 +421,10 @@ class Timer:
             torch.cuda.synchronize()
             return g
         except Exception:  # pragma: no cover - depends on the driver
-            torch.cuda.synchronize()
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
             return None
 
     def timed(self, step, steps, graph=None):
